@@ -1,0 +1,101 @@
+// Shared declarations for the deepcharuco_b200 CUDA sources (sm_100a only).
+//
+// Activation layout in HBM ("C4"): float [n][C/4][H][W][4] -- channels in groups of four, each group
+// a plane of float4 pixels.  Chosen for Blackwell: a TMA box {4, w, h, groups} of this tensor lands
+// in shared memory as the no-swizzle K-major core-matrix layout tcgen05.mma reads (8 pixels x 16 B
+// contiguous), at ANY pixel offset, so one halo tile serves all nine taps of a 3x3 convolution.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dcu {
+
+// ---- one 3x3 convolution layer, device-side view ---------------------------------------------------
+struct ConvParams {
+  const float* in;        // C4 [n][cin/4][hin][win][4]
+  float* out;             // C4 [n][cout_total/4][hout'][wout'][4]  (hout' after pool / upsample)
+  const float* bias;      // [cout_total]
+  const float* alpha;     // [cout_total]
+  const float* beta;      // [cout_total]
+  int n;                  // images (frames or patches)
+  int cin, cout_total;    // cout_total: channel count of the output tensor
+  int hin, win;           // input spatial size
+  int hout, wout;         // conv output size before pool/upsample (hin + 2*pad - 2)
+  int pad;                // 0 (valid) or 1 (same)
+  int pool;               // 1: 2x2 max-pool in the epilogue
+  int ups;                // 1: write each output to a 2x2 block (nearest x2 upsample)
+  // fused RefineNet head (convPa -> convPb 1x1 -> 64x64 arg-max), enabled when head_w != nullptr
+  const float* head_w;    // [64] convPb weight
+  float head_b;           // convPb bias
+  unsigned long long* head_key;  // [n] packed (orderable heat value << 32 | ~index)
+  float* heat;            // optional [n][hout][wout] dump of the heat map (tests), may be null
+};
+
+// FFMA path: weights packed [cin/4][9 taps][4 cin][cout_total] with the cout axis permuted per 64-block
+// so a thread's 8 channels are two float4 that are bank-conflict free (see conv_ffma.cu).
+struct FfmaWeights {
+  const float* w;
+};
+
+void launch_conv3x3_ffma(const ConvParams& p, const float* w_packed, cudaStream_t s);
+
+// first layer (cin == 1): direct convolution from u8 frames through the (x-128)/255 LUT, or from fp32 patches
+struct FirstConvParams {
+  const uint8_t* in_u8;   // [n][hin][win] or null
+  const float* in_f32;    // [n][hin][win] or null
+  const float* lut;       // [256] fp32 (x-128)/255, host-computed (model_utils.py:46-50)
+  float* out;             // C4 [n][16][hout][wout][4]
+  const float* w;         // [9][64]
+  const float* bias; const float* alpha; const float* beta;   // [64]
+  int n, hin, win, hout, wout, pad;
+};
+void launch_conv_first(const FirstConvParams& p, cudaStream_t s);
+
+// 1x1 heads of the detector (convPb 256->65, convDb 256->n_ids+1), NCHW outputs (net.py:74,77)
+struct HeadParams {
+  const float* in;        // C4 [n][128][h][w][4]: channels 0..255 = cPa, 256..511 = cDa
+  const float* w_loc;     // [65][256]
+  const float* b_loc;     // [65]
+  const float* w_ids;     // [n_ids+1][256]
+  const float* b_ids;     // [n_ids+1]
+  float* loc;             // [n][65][h][w]
+  float* ids;             // [n][n_ids+1][h][w]
+  int n, h, w, n_ids1;
+};
+void launch_heads_1x1(const HeadParams& p, cudaStream_t s);
+
+// decode + patch gather (model_utils.py:53-124, 19-36)
+struct DecodeParams {
+  const float* loc; const float* ids; const uint8_t* frames; const float* lut;
+  int n, H, W, h, w, n_ids1, dust_bin;
+  int append;
+  int32_t* counts; int32_t* offsets; int32_t* total; int32_t* kpts; float* patches;
+  int max_patches;
+  unsigned long long* scan_state;   // [max_batch] chained-scan cells
+  unsigned int epoch;
+};
+void launch_decode_gather(const DecodeParams& p, cudaStream_t s);
+size_t decode_smem_bytes(int cells);
+
+void launch_extract_patches(const float* image, int H, int W, const int32_t* xy, int k, float* patches, cudaStream_t s);
+
+// RefineNet tail: packed arg-max key -> (col,row) and refined (x,y)   (refinenet.py:111-114)
+void launch_refine_finalize(const unsigned long long* keys, const int32_t* xy, int xy_stride, int p,
+                            int32_t* corners, float* refined, cudaStream_t s);
+
+// layout converters used by the debug/test entry point
+void launch_nchw_to_c4(const float* in, float* out, int n, int c, int h, int w, cudaStream_t s);
+void launch_c4_to_nchw(const float* in, float* out, int n, int c, int h, int w, cudaStream_t s);
+
+// tcgen05 path (conv_tc.cu)
+struct TcLayerPack {
+  const float* w_blocks;  // per (chunk of 16 cin, tap): [hi|lo][4 k-groups][N][4] floats
+  int cin, cout;          // cout here = N handled per CTA pass (64 or 128)
+};
+int tc_supported_shape(int cin, int cout);
+cudaError_t launch_conv3x3_tc(const ConvParams& p, const float* w_blocks, int n_slices, const void* tmap_in,
+                              int sm_count, cudaStream_t s);
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace dcu

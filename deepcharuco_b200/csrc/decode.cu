@@ -1,0 +1,167 @@
+// Heat-map decode + corner-patch gather in ONE bandwidth-bound kernel.
+//
+// Per frame (one CTA): per-cell arg-max over the 65 loc and n_ids+1 ids logits (first max wins),
+// dustbin filter, cell -> pixel, ordered compaction, then the 24x24 patch gather with implicit zero
+// padding.  Restates, for a whole batch and without a host round trip:
+//   pred_argmax          /root/reference/src/models/model_utils.py:72-78
+//   label_to_keypoints   model_utils.py:108-124   (x = 8*col + p%8, y = 8*row + p//8)
+//   extract_patches      model_utils.py:19-36     (pad 12 with 0.0 of the normalised image)
+//   sort by id (stable)  /root/reference/src/inference.py:68-69
+// Memory behaviour: the logits are read once, channel-strided so consecutive threads read consecutive
+// cells of one channel plane (fully coalesced 128 B lines); patches are written as coalesced fp32 rows.
+// Frames get their output rows by a chained (look-back) scan over frame index, so row numbering is
+// deterministic and needs no second launch.
+#include "common.cuh"
+
+namespace dcu {
+
+constexpr int D_THREADS = 256;
+
+size_t decode_smem_bytes(int cells) { return (size_t)cells * 4 * sizeof(uint32_t); }
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(D_THREADS)
+decode_gather_kernel(DecodeParams p) {
+  extern __shared__ __align__(16) uint32_t dsm[];
+  const int cells = p.h * p.w;
+  uint32_t* key_u = dsm;                 // unsorted keys  (id * cells + cell)
+  uint32_t* pix_u = dsm + cells;         // unsorted sub-cell pixel index 0..63
+  uint32_t* key_s = dsm + 2 * cells;     // sorted keys
+  uint32_t* xy_s = dsm + 3 * cells;      // sorted x | y << 16
+  __shared__ int s_count;
+  __shared__ int s_base;
+  const int f = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+
+  // ---- phase 1: per-cell arg-max + dustbin filter ------------------------------------------------
+  const float* loc = p.loc + (size_t)f * 65 * cells;
+  const float* ids = p.ids + (size_t)f * p.n_ids1 * cells;
+  for (int c = tid; c < cells; c += D_THREADS) {
+    float best = loc[c];
+    int la = 0;
+#pragma unroll 8
+    for (int ch = 1; ch < 65; ++ch) {
+      const float v = loc[(size_t)ch * cells + c];
+      if (v > best) { best = v; la = ch; }        // strict '>' keeps the FIRST maximum (torch.argmax)
+    }
+    float bi = ids[c];
+    int ia = 0;
+    for (int ch = 1; ch < p.n_ids1; ++ch) {
+      const float v = ids[(size_t)ch * cells + c];
+      if (v > bi) { bi = v; ia = ch; }
+    }
+    if (la == 64) ia = p.dust_bin;                // model_utils.py:77 (loc dustbin hard-coded 64)
+    if (ia != p.dust_bin) {                        // model_utils.py:111
+      const int slot = atomicAdd(&s_count, 1);
+      key_u[slot] = (uint32_t)ia * (uint32_t)cells + (uint32_t)c;
+      pix_u[slot] = (uint32_t)la;
+    }
+  }
+  __syncthreads();
+  const int K = s_count;
+
+  // ---- phase 2: rank sort by (id, cell); keys are unique -----------------------------------------
+  for (int i = tid; i < K; i += D_THREADS) {
+    const uint32_t k = key_u[i];
+    int rank = 0;
+    for (int j = 0; j < K; ++j) rank += (key_u[j] < k) ? 1 : 0;
+    const int cell = (int)(k % (uint32_t)cells);
+    const int cx = cell % p.w, cy = cell / p.w;
+    const uint32_t pp = pix_u[i];
+    const uint32_t x = 8u * cx + (pp & 7u), y = 8u * cy + (pp >> 3);
+    key_s[rank] = k;
+    xy_s[rank] = x | (y << 16);
+  }
+
+  // ---- phase 3: chained scan over frames -> base row ---------------------------------------------
+  if (tid == 0) {
+    const unsigned long long tag_agg = ((unsigned long long)(p.epoch * 4u + 1u)) << 32;
+    const unsigned long long tag_inc = ((unsigned long long)(p.epoch * 4u + 2u)) << 32;
+    int excl = 0;
+    if (f == 0) {
+      excl = p.append ? p.total[0] : 0;
+    } else {
+      atomicExch(&p.scan_state[f], tag_agg | (unsigned int)K);
+      int look = f - 1;
+      while (true) {
+        const unsigned long long st = ld_volatile_u64(&p.scan_state[look]);
+        const unsigned long long tag = st & 0xffffffff00000000ull;
+        if (tag == tag_inc) { excl += (int)(unsigned int)st; break; }
+        if (tag == tag_agg) { excl += (int)(unsigned int)st; --look; continue; }   // look >= 1 here: frame 0 only publishes inclusive
+        __nanosleep(40);
+      }
+    }
+    __threadfence();
+    atomicExch(&p.scan_state[f], tag_inc | (unsigned int)(excl + K));
+    p.counts[f] = K;
+    p.offsets[f] = excl;
+    if (f == p.n - 1) p.total[0] = excl + K;
+    s_base = excl;
+  }
+  __syncthreads();
+  const int base = s_base;
+
+  // ---- phase 4: keypoint rows --------------------------------------------------------------------
+  for (int j = tid; j < K; j += D_THREADS) {
+    const int row = base + j;
+    if (row < p.max_patches) {
+      const uint32_t k = key_s[j], xy = xy_s[j];
+      int4 rec;
+      rec.x = (int)(xy & 0xffffu); rec.y = (int)(xy >> 16);
+      rec.z = (int)(k / (uint32_t)cells); rec.w = (int)(k % (uint32_t)cells);
+      reinterpret_cast<int4*>(p.kpts)[row] = rec;
+    }
+  }
+
+  // ---- phase 5: 24x24 patch gather (window [y-12, y+12) x [x-12, x+12), zeros outside) -----------
+  if (p.patches != nullptr) {
+    const uint8_t* frame = p.frames + (size_t)f * p.H * p.W;
+    const int total_el = K * 576;
+    for (int e = tid; e < total_el; e += D_THREADS) {
+      const int j = e / 576, q = e - j * 576;
+      const int row = base + j;
+      if (row >= p.max_patches) break;
+      const uint32_t xy = xy_s[j];
+      const int py = q / 24, px = q - py * 24;
+      const int gy = (int)(xy >> 16) - 12 + py, gx = (int)(xy & 0xffffu) - 12 + px;
+      float v = 0.f;
+      if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) v = __ldg(p.lut + frame[(size_t)gy * p.W + gx]);
+      p.patches[(size_t)row * 576 + q] = v;
+    }
+  }
+}
+
+void launch_decode_gather(const DecodeParams& p, cudaStream_t s) {
+  if (p.n <= 0) return;
+  const size_t smem = decode_smem_bytes(p.h * p.w);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(decode_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  decode_gather_kernel<<<p.n, D_THREADS, smem, s>>>(p);
+}
+
+// stand-alone extract_patches on a normalised fp32 image (model_utils.py:19-36)
+__global__ void extract_patches_kernel(const float* image, int H, int W, const int32_t* xy, int k, float* patches) {
+  const int j = blockIdx.x;
+  if (j >= k) return;
+  const int x = xy[2 * j], y = xy[2 * j + 1];
+  for (int q = threadIdx.x; q < 576; q += blockDim.x) {
+    const int py = q / 24, px = q - py * 24;
+    const int gy = y - 12 + py, gx = x - 12 + px;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = image[(size_t)gy * W + gx];
+    patches[(size_t)j * 576 + q] = v;
+  }
+}
+void launch_extract_patches(const float* image, int H, int W, const int32_t* xy, int k, float* patches, cudaStream_t s) {
+  if (k <= 0) return;
+  extract_patches_kernel<<<k, 192, 0, s>>>(image, H, W, xy, k, patches);
+}
+
+}  // namespace dcu

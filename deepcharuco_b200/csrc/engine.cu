@@ -1,0 +1,764 @@
+// Engine + C ABI (include/deepcharuco_b200.h).  Owns packed weights, workspace, TMA descriptors and
+// the launch sequence  detector -> decode+gather -> RefineNet  that replaces the body of
+// inference.infer_image (/root/reference/src/inference.py:41-60) for whole batches.
+#include <cuda_runtime.h>
+#include <cuda.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/deepcharuco_b200.h"
+#include "common.cuh"
+
+using namespace dcu;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(DCU_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(_e) + " (" + \
+                                    __FILE__ + ":" + std::to_string(__LINE__) + ")");              \
+  } while (0)
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t alloc(size_t b) {
+    bytes = b;
+    return cudaMalloc(&p, b ? b : 16);
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// One 3x3 layer with cin % 4 == 0 (everything except the two first layers and the 1x1 heads)
+struct Layer3x3 {
+  int cin = 0, cout = 0;      // cout = total output channels (Pa|Da merged: 512)
+  int pad = 1, pool = 0, ups = 0;
+  DevBuf w_ffma;              // [cin/4][9][4][cout]
+  DevBuf w_tc;                // tcgen05 blocks (conv_tc.cu layout), empty if shape unsupported
+  int tc_nt = 0;              // N per CTA pass for the tcgen05 kernel (64 / 128), 0 = unsupported
+  DevBuf bias, alpha, beta;   // [cout]
+};
+
+struct FirstLayer {
+  DevBuf w, bias, alpha, beta;   // [9][64], [64] x3
+  int pad = 1;
+};
+
+std::vector<float> pack_ffma(const std::vector<const float*>& ws, const std::vector<int>& couts, int cin) {
+  // OIHW (possibly several tensors concatenated along O) -> [cin/4][tap][c][cout_total]
+  int cout_total = 0;
+  for (int c : couts) cout_total += c;
+  std::vector<float> out((size_t)cin * 9 * cout_total);
+  int obase = 0;
+  for (size_t t = 0; t < ws.size(); ++t) {
+    for (int o = 0; o < couts[t]; ++o)
+      for (int i = 0; i < cin; ++i)
+        for (int tap = 0; tap < 9; ++tap)
+          out[(((size_t)(i >> 2) * 9 + tap) * 4 + (i & 3)) * cout_total + obase + o] =
+              ws[t][((size_t)o * cin + i) * 9 + tap];
+    obase += couts[t];
+  }
+  return out;
+}
+
+std::vector<float> concat(const std::vector<const float*>& v, const std::vector<int>& n) {
+  std::vector<float> out;
+  for (size_t i = 0; i < v.size(); ++i) out.insert(out.end(), v[i], v[i] + n[i]);
+  return out;
+}
+
+cudaError_t upload(DevBuf& b, const std::vector<float>& h) {
+  cudaError_t e = b.alloc(h.size() * sizeof(float));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(b.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
+}
+
+// hi/lo split used by the tcgen05 path: round-to-nearest to 10 explicit mantissa bits (TF32)
+inline float tf32_rn(float x) {
+  uint32_t b; std::memcpy(&b, &x, 4);
+  b = (b + 0x1000u) & 0xffffe000u;
+  float r; std::memcpy(&r, &b, 4);
+  return r;
+}
+
+// tcgen05 weight blocks: for slice s (NT output channels), chunk q (16 input channels), tap t:
+//   block[(s*chunks + q)*9 + t] = { hi[4 kgroups][NT][4], lo[4 kgroups][NT][4] }   (floats)
+std::vector<float> pack_tc(const std::vector<const float*>& ws, const std::vector<int>& couts, int cin, int nt) {
+  int cout_total = 0;
+  for (int c : couts) cout_total += c;
+  const int slices = cout_total / nt, chunks = cin / 16;
+  const size_t blk = (size_t)2 * 4 * nt * 4;
+  std::vector<float> out((size_t)slices * chunks * 9 * blk);
+  std::vector<const float*> row(cout_total);
+  {
+    int o = 0;
+    for (size_t t = 0; t < ws.size(); ++t)
+      for (int k = 0; k < couts[t]; ++k) row[o++] = ws[t] + (size_t)k * cin * 9;
+  }
+  for (int s = 0; s < slices; ++s)
+    for (int q = 0; q < chunks; ++q)
+      for (int tap = 0; tap < 9; ++tap) {
+        float* b = out.data() + (((size_t)s * chunks + q) * 9 + tap) * blk;
+        for (int kg = 0; kg < 4; ++kg)
+          for (int n = 0; n < nt; ++n)
+            for (int e = 0; e < 4; ++e) {
+              const int ci = q * 16 + kg * 4 + e;
+              const float w = row[s * nt + n][(size_t)ci * 9 + tap];
+              const float hi = tf32_rn(w);
+              const float lo = tf32_rn(w - hi);
+              b[((size_t)kg * nt + n) * 4 + e] = hi;
+              b[(size_t)4 * nt * 4 + ((size_t)kg * nt + n) * 4 + e] = lo;
+            }
+      }
+  return out;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+// tile arrangement chosen for the tcgen05 kernel (conv_tc.cu): MT m-tiles of 16x8 pixels as TR x TC
+struct TcGeom { int tr, tc; };
+static TcGeom tc_geom(int nt, int hout, int wout) {
+  if (nt == 64) {               // MT = 4
+    if (wout >= 32) return {1, 4};
+    if (hout > 16 && wout > 8) return {2, 2};
+    return {1, 4};
+  }
+  // MT = 2
+  if (wout % 16 == 0 || wout > 40) return {1, 2};
+  if (hout > 16) return {2, 1};
+  return {1, 2};
+}
+
+struct DcuEngine {
+  DcuConfig cfg{};
+  int sm_count = 148;
+  int conv_impl = DCU_CONV_FFMA;
+  bool has_ref = false;
+  int64_t launches = 0;
+
+  // detector
+  FirstLayer det_first;
+  Layer3x3 det[8];              // 1b,2a,2b,3a,3b,4a,4b,(Pa|Da)
+  DevBuf w_loc, b_loc, w_ids, b_ids;
+  // refinenet
+  FirstLayer ref_first;
+  Layer3x3 ref[10];             // 1b,2a,2b,3a,3b,4a,4b,5a,5b,Pa
+  DevBuf ref_head_w; float ref_head_b = 0.f;
+
+  DevBuf lut;                   // [256] (x-128)/255
+  int mb1 = 4, mb2 = 32, rp = 64;   // micro-batch sizes: full-res layers, low-res layers, RefineNet patches
+  DevBuf act[2];                // ping-pong activation buffers
+  DevBuf stage2_in;             // conv2b output for mb2 frames (input of conv3a)
+  DevBuf heads;                 // (Pa|Da) output for mb2 frames
+  DevBuf loc, ids;              // [mb2] logits when the caller does not want them
+  DevBuf counts, offsets, total, kpts, patches, keys, refined, scan_state, frames;
+  unsigned int epoch = 1;
+  // optional per-launch event timing (dcu_profile_*)
+  struct ProfRec { cudaEvent_t a, b; double work; int cls; };
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t get_event() {
+    if (!ev_pool.empty()) { cudaEvent_t ev = ev_pool.back(); ev_pool.pop_back(); return ev; }
+    cudaEvent_t ev; cudaEventCreate(&ev); return ev;
+  }
+  void prof_begin(int cls, double work, cudaStream_t s) {
+    if (!profiling) return;
+    ProfRec r{get_event(), get_event(), work, cls};
+    cudaEventRecord(r.a, s);
+    prof.push_back(r);
+  }
+  void prof_end(cudaStream_t s) {
+    if (!profiling) return;
+    cudaEventRecord(prof.back().b, s);
+  }
+  // pinned staging (host entry point)
+  uint8_t* h_frames = nullptr; int32_t* h_counts = nullptr; int32_t* h_offsets = nullptr;
+  int32_t* h_kpts = nullptr; float* h_refined = nullptr; int32_t* h_total = nullptr;
+
+  ~DcuEngine() {
+    DevBuf* all[] = {&w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
+                     &ids, &counts, &offsets, &total, &kpts, &patches, &keys, &refined, &scan_state, &frames};
+    for (DevBuf* b : all) b->release();
+    FirstLayer* fl[] = {&det_first, &ref_first};
+    for (FirstLayer* f : fl) { f->w.release(); f->bias.release(); f->alpha.release(); f->beta.release(); }
+    for (Layer3x3& l : det) { l.w_ffma.release(); l.w_tc.release(); l.bias.release(); l.alpha.release(); l.beta.release(); }
+    for (Layer3x3& l : ref) { l.w_ffma.release(); l.w_tc.release(); l.bias.release(); l.alpha.release(); l.beta.release(); }
+    for (auto& r : prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto ev : ev_pool) cudaEventDestroy(ev);
+    if (h_frames) cudaFreeHost(h_frames);
+    if (h_counts) cudaFreeHost(h_counts);
+    if (h_offsets) cudaFreeHost(h_offsets);
+    if (h_kpts) cudaFreeHost(h_kpts);
+    if (h_refined) cudaFreeHost(h_refined);
+    if (h_total) cudaFreeHost(h_total);
+  }
+};
+
+namespace {
+
+int build_first(FirstLayer& f, const DcuConvLayer& L, int pad) {
+  if (L.cin != 1 || L.cout != 64 || L.ksize != 3 || !L.alpha || !L.beta)
+    return fail(DCU_ERR_INVALID, "first layer must be 1->64 3x3 with BN");
+  std::vector<float> w(9 * 64);
+  for (int o = 0; o < 64; ++o)
+    for (int t = 0; t < 9; ++t) w[t * 64 + o] = L.weight[o * 9 + t];
+  f.pad = pad;
+  CK(upload(f.w, w));
+  CK(upload(f.bias, std::vector<float>(L.bias, L.bias + 64)));
+  CK(upload(f.alpha, std::vector<float>(L.alpha, L.alpha + 64)));
+  CK(upload(f.beta, std::vector<float>(L.beta, L.beta + 64)));
+  return DCU_OK;
+}
+
+int build_3x3(Layer3x3& l, std::vector<const DcuConvLayer*> parts, int pad, int pool, int ups) {
+  std::vector<const float*> ws, bs, as, es;
+  std::vector<int> couts;
+  int cin = parts[0]->cin;
+  for (const DcuConvLayer* L : parts) {
+    if (L->ksize != 3 || L->cin != cin || (cin % 16) != 0 || (L->cout % 64) != 0 || !L->alpha || !L->beta)
+      return fail(DCU_ERR_INVALID, "unsupported 3x3 layer shape");
+    ws.push_back(L->weight); bs.push_back(L->bias); as.push_back(L->alpha); es.push_back(L->beta);
+    couts.push_back(L->cout);
+  }
+  l.cin = cin; l.cout = 0;
+  for (int c : couts) l.cout += c;
+  l.pad = pad; l.pool = pool; l.ups = ups;
+  CK(upload(l.w_ffma, pack_ffma(ws, couts, cin)));
+  CK(upload(l.bias, concat(bs, couts)));
+  CK(upload(l.alpha, concat(as, couts)));
+  CK(upload(l.beta, concat(es, couts)));
+  l.tc_nt = tc_supported_shape(cin, l.cout);
+  if (l.tc_nt > 0) CK(upload(l.w_tc, pack_tc(ws, couts, cin, l.tc_nt)));
+  return DCU_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// layer runners
+// ---------------------------------------------------------------------------------------------------
+static int make_tmap(CUtensorMap* tm, const float* base, int n, int cin, int h, int w, int box_w, int box_h) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[5] = {4, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)(cin / 4), (cuuint64_t)n};
+  cuuint64_t strides[4] = {16, (cuuint64_t)w * 16, (cuuint64_t)w * h * 16, (cuuint64_t)w * h * 16 * (cin / 4)};
+  cuuint32_t box[5] = {4, (cuuint32_t)box_w, (cuuint32_t)box_h, 4, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return DCU_OK;
+}
+
+struct HeadFuse { const float* w = nullptr; float b = 0.f; unsigned long long* keys = nullptr; float* heat = nullptr; };
+
+static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, float* out, int n, int hin, int win,
+                   const HeadFuse* hf, cudaStream_t s) {
+  ConvParams p{};
+  p.in = in; p.out = out; p.bias = l.bias.as<float>(); p.alpha = l.alpha.as<float>(); p.beta = l.beta.as<float>();
+  p.n = n; p.cin = l.cin; p.cout_total = l.cout; p.hin = hin; p.win = win;
+  p.hout = hin + 2 * l.pad - 2; p.wout = win + 2 * l.pad - 2; p.pad = l.pad; p.pool = l.pool; p.ups = l.ups;
+  if (hf) { p.head_w = hf->w; p.head_b = hf->b; p.head_key = hf->keys; p.heat = hf->heat; }
+  if (n <= 0) return DCU_OK;
+  e->prof_begin(0, 2.0 * 9.0 * l.cin * l.cout * (double)p.hout * p.wout * n, s);
+  if (impl == DCU_CONV_TCGEN05) {
+    if (l.tc_nt == 0) return fail(DCU_ERR_UNSUPPORTED, "layer shape not supported by the tcgen05 kernel");
+    const TcGeom g = tc_geom(l.tc_nt, p.hout, p.wout);
+    CUtensorMap tm;
+    int rc = make_tmap(&tm, in, n, l.cin, hin, win, 8 * g.tc + 2, 16 * g.tr + 2);
+    if (rc) return rc;
+    cudaError_t ce = launch_conv3x3_tc(p, l.w_tc.as<float>(), l.cout / l.tc_nt, &tm, e->sm_count, s);
+    if (ce != cudaSuccess) return fail(DCU_ERR_CUDA, std::string("tcgen05 conv launch: ") + cudaGetErrorString(ce));
+  } else {
+    launch_conv3x3_ffma(p, l.w_ffma.as<float>(), s);
+  }
+  e->prof_end(s);
+  e->launches++;
+  CK(cudaGetLastError());
+  return DCU_OK;
+}
+
+static int run_first(DcuEngine* e, const FirstLayer& f, const uint8_t* in_u8, const float* in_f32, float* out, int n,
+                     int hin, int win, cudaStream_t s) {
+  FirstConvParams p{};
+  p.in_u8 = in_u8; p.in_f32 = in_f32; p.lut = e->lut.as<float>(); p.out = out; p.w = f.w.as<float>();
+  p.bias = f.bias.as<float>(); p.alpha = f.alpha.as<float>(); p.beta = f.beta.as<float>();
+  p.n = n; p.hin = hin; p.win = win; p.pad = f.pad; p.hout = hin + 2 * f.pad - 2; p.wout = win + 2 * f.pad - 2;
+  if (n <= 0) return DCU_OK;
+  e->prof_begin(1, 2.0 * 9.0 * 64 * (double)p.hout * p.wout * n, s);
+  launch_conv_first(p, s);
+  e->prof_end(s);
+  e->launches++;
+  CK(cudaGetLastError());
+  return DCU_OK;
+}
+
+// detector on n <= mb2 frames: loc/ids NCHW out
+static int detector_group(DcuEngine* e, const uint8_t* frames, const float* images, int n, float* loc, float* ids,
+                          cudaStream_t s) {
+  const int H = e->cfg.height, W = e->cfg.width;
+  float* a0 = e->act[0].as<float>();
+  float* a1 = e->act[1].as<float>();
+  float* s2 = e->stage2_in.as<float>();
+  const size_t s2_frame = (size_t)64 * (H / 4) * (W / 4);
+  int rc;
+  for (int f0 = 0; f0 < n; f0 += e->mb1) {
+    const int m = std::min(e->mb1, n - f0);
+    if ((rc = run_first(e, e->det_first, frames ? frames + (size_t)f0 * H * W : nullptr,
+                        images ? images + (size_t)f0 * H * W : nullptr, a0, m, H, W, s))) return rc;          // conv1a
+    if ((rc = run_3x3(e, e->det[0], e->conv_impl, a0, a1, m, H, W, nullptr, s))) return rc;                     // conv1b + pool
+    if ((rc = run_3x3(e, e->det[1], e->conv_impl, a1, a0, m, H / 2, W / 2, nullptr, s))) return rc;             // conv2a
+    if ((rc = run_3x3(e, e->det[2], e->conv_impl, a0, s2 + f0 * s2_frame, m, H / 2, W / 2, nullptr, s))) return rc;  // conv2b + pool
+  }
+  if ((rc = run_3x3(e, e->det[3], e->conv_impl, s2, a0, n, H / 4, W / 4, nullptr, s))) return rc;               // conv3a
+  if ((rc = run_3x3(e, e->det[4], e->conv_impl, a0, a1, n, H / 4, W / 4, nullptr, s))) return rc;               // conv3b + pool
+  if ((rc = run_3x3(e, e->det[5], e->conv_impl, a1, a0, n, H / 8, W / 8, nullptr, s))) return rc;               // conv4a
+  if ((rc = run_3x3(e, e->det[6], e->conv_impl, a0, a1, n, H / 8, W / 8, nullptr, s))) return rc;               // conv4b
+  if ((rc = run_3x3(e, e->det[7], e->conv_impl, a1, e->heads.as<float>(), n, H / 8, W / 8, nullptr, s))) return rc;  // convPa | convDa
+  HeadParams hp{};
+  hp.in = e->heads.as<float>(); hp.w_loc = e->w_loc.as<float>(); hp.b_loc = e->b_loc.as<float>();
+  hp.w_ids = e->w_ids.as<float>(); hp.b_ids = e->b_ids.as<float>(); hp.loc = loc; hp.ids = ids;
+  hp.n = n; hp.h = H / 8; hp.w = W / 8; hp.n_ids1 = e->cfg.n_ids + 1;
+  e->prof_begin(2, 2.0 * 256.0 * (65 + hp.n_ids1) * (double)hp.h * hp.w * n, s);
+  launch_heads_1x1(hp, s);                                                                                       // convPb, convDb
+  e->prof_end(s);
+  e->launches++;
+  CK(cudaGetLastError());
+  return DCU_OK;
+}
+
+static int decode_group(DcuEngine* e, const float* loc, const float* ids, const uint8_t* frames, int n, int dust_bin,
+                        int append, int32_t* counts, int32_t* offsets, int32_t* total, int32_t* kpts, float* patches,
+                        cudaStream_t s) {
+  DecodeParams d{};
+  d.loc = loc; d.ids = ids; d.frames = frames; d.lut = e->lut.as<float>();
+  d.n = n; d.H = e->cfg.height; d.W = e->cfg.width; d.h = d.H / 8; d.w = d.W / 8; d.n_ids1 = e->cfg.n_ids + 1;
+  d.dust_bin = dust_bin; d.append = append; d.counts = counts; d.offsets = offsets; d.total = total; d.kpts = kpts;
+  d.patches = patches; d.max_patches = e->cfg.max_patches; d.scan_state = e->scan_state.as<unsigned long long>();
+  d.epoch = e->epoch++;
+  // algorithmic bytes: logits read once; + K*(2304 read + 2304 written + 16) added by the caller's K
+  e->prof_begin(3, (double)(65 + d.n_ids1) * d.h * d.w * 4.0 * n, s);
+  launch_decode_gather(d, s);
+  e->prof_end(s);
+  e->launches++;
+  CK(cudaGetLastError());
+  return DCU_OK;
+}
+
+// RefineNet on p patches (any p; processed in chunks of rp)
+static int refine_run(DcuEngine* e, const float* patches, const int32_t* xy, int xy_stride, int p, int32_t* corners,
+                      float* refined, float* heat, cudaStream_t s) {
+  float* a0 = e->act[0].as<float>();
+  float* a1 = e->act[1].as<float>();
+  int rc;
+  for (int p0 = 0; p0 < p; p0 += e->rp) {
+    const int m = std::min(e->rp, p - p0);
+    unsigned long long* keys = e->keys.as<unsigned long long>() + p0;
+    CK(cudaMemsetAsync(keys, 0, (size_t)m * sizeof(unsigned long long), s));
+    if ((rc = run_first(e, e->ref_first, nullptr, patches + (size_t)p0 * 576, a0, m, 24, 24, s))) return rc;   // conv1a -> 22
+    if ((rc = run_3x3(e, e->ref[0], e->conv_impl, a0, a1, m, 22, 22, nullptr, s))) return rc;   // conv1b -> 20
+    if ((rc = run_3x3(e, e->ref[1], e->conv_impl, a1, a0, m, 20, 20, nullptr, s))) return rc;   // conv2a -> 18
+    if ((rc = run_3x3(e, e->ref[2], e->conv_impl, a0, a1, m, 18, 18, nullptr, s))) return rc;   // conv2b -> 16 -> pool 8
+    if ((rc = run_3x3(e, e->ref[3], e->conv_impl, a1, a0, m, 8, 8, nullptr, s))) return rc;     // conv3a
+    if ((rc = run_3x3(e, e->ref[4], e->conv_impl, a0, a1, m, 8, 8, nullptr, s))) return rc;     // conv3b -> up 16
+    if ((rc = run_3x3(e, e->ref[5], e->conv_impl, a1, a0, m, 16, 16, nullptr, s))) return rc;   // conv4a
+    if ((rc = run_3x3(e, e->ref[6], e->conv_impl, a0, a1, m, 16, 16, nullptr, s))) return rc;   // conv4b -> up 32
+    if ((rc = run_3x3(e, e->ref[7], e->conv_impl, a1, a0, m, 32, 32, nullptr, s))) return rc;   // conv5a
+    if ((rc = run_3x3(e, e->ref[8], e->conv_impl, a0, a1, m, 32, 32, nullptr, s))) return rc;   // conv5b -> up 64
+    HeadFuse hf;
+    hf.w = e->ref_head_w.as<float>(); hf.b = e->ref_head_b; hf.keys = keys;
+    hf.heat = heat ? heat + (size_t)p0 * 4096 : nullptr;
+    if ((rc = run_3x3(e, e->ref[9], e->conv_impl, a1, nullptr, m, 64, 64, &hf, s))) return rc;  // convPa + convPb + arg-max
+    e->prof_begin(4, 0.0, s);
+    launch_refine_finalize(keys, xy + (size_t)p0 * xy_stride, xy_stride, m, corners ? corners + 2 * (size_t)p0 : nullptr,
+                           refined + 2 * (size_t)p0, s);
+    e->prof_end(s);
+    e->launches++;
+    CK(cudaGetLastError());
+  }
+  return DCU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* dcu_last_error(void) { return g_err.c_str(); }
+const char* dcu_version(void) { return "deepcharuco_b200 0.1 (sm_100a)"; }
+
+int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const DcuConvLayer* R, int n_ref,
+               DcuEngine** out) {
+  if (!cfg || !D || !out || n_det != 12) return fail(DCU_ERR_INVALID, "dcu_create: need 12 detector layers");
+  if (cfg->height % 8 || cfg->width % 8 || cfg->height < 24 || cfg->width < 24)
+    return fail(DCU_ERR_INVALID, "dcu_create: height/width must be multiples of 8 (>= 24)");
+  if (cfg->n_ids < 1 || cfg->n_ids > 30 || cfg->max_batch < 1 || cfg->max_patches < 1)
+    return fail(DCU_ERR_INVALID, "dcu_create: bad n_ids / max_batch / max_patches");
+  if (cfg->width > 65535 || cfg->height > 65535) return fail(DCU_ERR_INVALID, "dcu_create: frame too large");
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(DCU_ERR_UNSUPPORTED, "deepcharuco_b200 needs an sm_100 (B200) device");
+  DcuEngine* e = new DcuEngine();
+  e->cfg = *cfg;
+  e->sm_count = prop.multiProcessorCount;
+  e->conv_impl = cfg->conv_impl;
+  int rc;
+#define TRY(x) do { if ((rc = (x)) != DCU_OK) { delete e; return rc; } } while (0)
+#define TRYC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { delete e; return fail(DCU_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); } } while (0)
+  // detector: conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db  (net.py:22-48)
+  TRY(build_first(e->det_first, D[0], 1));
+  const int pools[7] = {1, 0, 1, 0, 1, 0, 0};
+  for (int i = 0; i < 7; ++i) TRY(build_3x3(e->det[i], {&D[1 + i]}, 1, pools[i], 0));
+  TRY(build_3x3(e->det[7], {&D[8], &D[10]}, 1, 0, 0));
+  if (D[9].ksize != 1 || D[9].cin != 256 || D[9].cout != 65 || D[11].ksize != 1 || D[11].cin != 256 ||
+      D[11].cout != cfg->n_ids + 1 || D[8].cout != 256 || D[10].cout != 256) {
+    delete e;
+    return fail(DCU_ERR_INVALID, "dcu_create: head shapes do not match n_ids");
+  }
+  TRYC(upload(e->w_loc, std::vector<float>(D[9].weight, D[9].weight + 65 * 256)));
+  TRYC(upload(e->b_loc, std::vector<float>(D[9].bias, D[9].bias + 65)));
+  TRYC(upload(e->w_ids, std::vector<float>(D[11].weight, D[11].weight + (size_t)(cfg->n_ids + 1) * 256)));
+  TRYC(upload(e->b_ids, std::vector<float>(D[11].bias, D[11].bias + cfg->n_ids + 1)));
+  // refinenet: conv1a,1b,2a,2b,3a,3b,4a,4b,5a,5b,Pa,Pb  (refinenet.py:22-47)
+  e->has_ref = (R != nullptr && n_ref == 12);
+  if (R != nullptr && n_ref != 0 && n_ref != 12) { delete e; return fail(DCU_ERR_INVALID, "dcu_create: need 12 RefineNet layers"); }
+  if (e->has_ref) {
+    TRY(build_first(e->ref_first, R[0], 0));
+    const int rpad[10] = {0, 0, 0, 1, 1, 1, 1, 1, 1, 1};
+    const int rpool[10] = {0, 0, 1, 0, 0, 0, 0, 0, 0, 0};
+    const int rups[10] = {0, 0, 0, 0, 1, 0, 1, 0, 1, 0};
+    for (int i = 0; i < 10; ++i) TRY(build_3x3(e->ref[i], {&R[1 + i]}, rpad[i], rpool[i], rups[i]));
+    if (R[11].ksize != 1 || R[11].cin != 64 || R[11].cout != 1 || R[10].cout != 64) {
+      delete e;
+      return fail(DCU_ERR_INVALID, "dcu_create: RefineNet head shape");
+    }
+    TRYC(upload(e->ref_head_w, std::vector<float>(R[11].weight, R[11].weight + 64)));
+    e->ref_head_b = R[11].bias[0];
+  }
+  // (x - 128) / 255 in fp32 with a true division, as numpy does (model_utils.py:48-49)
+  {
+    std::vector<float> lut(256);
+    for (int i = 0; i < 256; ++i) lut[i] = ((float)i - 128.0f) / 255.0f;
+    TRYC(upload(e->lut, lut));
+  }
+  // workspace
+  const int H = cfg->height, W = cfg->width;
+  const double area = (double)H * W / (320.0 * 240.0);
+  e->mb1 = std::max(1, (int)std::floor(4.0 / area + 1e-9));
+  e->mb2 = std::max(e->mb1, (int)std::floor(32.0 / area + 1e-9));
+  if (const char* v = getenv("DCU_MB1")) e->mb1 = std::max(1, atoi(v));
+  if (const char* v = getenv("DCU_MB2")) e->mb2 = std::max(1, atoi(v));
+  if (const char* v = getenv("DCU_RP")) e->rp = std::max(1, atoi(v));
+  e->mb2 = std::max(e->mb2, e->mb1);
+  e->mb2 = (e->mb2 / e->mb1) * e->mb1;
+  const size_t det_full = (size_t)e->mb1 * 64 * H * W;                       // conv1a out (floats)
+  const size_t det_low = (size_t)e->mb2 * 128 * (H / 4) * (W / 4);           // conv3a out
+  const size_t ref_big = e->has_ref ? (size_t)e->rp * 64 * 64 * 64 : 0;      // conv5b upsampled
+  const size_t act_floats = std::max(std::max(det_full, det_low), ref_big);
+  TRYC(e->act[0].alloc(act_floats * 4));
+  TRYC(e->act[1].alloc(act_floats * 4));
+  TRYC(e->stage2_in.alloc((size_t)e->mb2 * 64 * (H / 4) * (W / 4) * 4));
+  TRYC(e->heads.alloc((size_t)e->mb2 * 512 * (H / 8) * (W / 8) * 4));
+  TRYC(e->loc.alloc((size_t)e->mb2 * 65 * (H / 8) * (W / 8) * 4));
+  TRYC(e->ids.alloc((size_t)e->mb2 * (cfg->n_ids + 1) * (H / 8) * (W / 8) * 4));
+  TRYC(e->counts.alloc((size_t)cfg->max_batch * 4));
+  TRYC(e->offsets.alloc((size_t)cfg->max_batch * 4));
+  TRYC(e->total.alloc(16));
+  TRYC(e->kpts.alloc((size_t)cfg->max_patches * 16));
+  TRYC(e->patches.alloc((size_t)cfg->max_patches * 576 * 4));
+  TRYC(e->keys.alloc((size_t)cfg->max_patches * 8));
+  TRYC(e->refined.alloc((size_t)cfg->max_patches * 8));
+  TRYC(e->scan_state.alloc((size_t)std::max(cfg->max_batch, e->mb2) * 8));
+  TRYC(cudaMemset(e->scan_state.p, 0, e->scan_state.bytes));
+  TRYC(cudaMemset(e->total.p, 0, 16));
+  TRYC(e->frames.alloc((size_t)cfg->max_batch * H * W));
+  TRYC(cudaMallocHost(&e->h_frames, (size_t)cfg->max_batch * H * W));
+  TRYC(cudaMallocHost(&e->h_counts, (size_t)cfg->max_batch * 4));
+  TRYC(cudaMallocHost(&e->h_offsets, (size_t)cfg->max_batch * 4));
+  TRYC(cudaMallocHost(&e->h_kpts, (size_t)cfg->max_patches * 16));
+  TRYC(cudaMallocHost(&e->h_refined, (size_t)cfg->max_patches * 8));
+  TRYC(cudaMallocHost(&e->h_total, 16));
+  TRYC(cudaDeviceSynchronize());
+#undef TRY
+#undef TRYC
+  *out = e;
+  return DCU_OK;
+}
+
+int dcu_destroy(DcuEngine* e) {
+  if (!e) return DCU_OK;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  delete e;
+  return DCU_OK;
+}
+
+int dcu_set_conv_impl(DcuEngine* e, int impl) {
+  if (!e || (impl != DCU_CONV_FFMA && impl != DCU_CONV_TCGEN05)) return fail(DCU_ERR_INVALID, "bad conv_impl");
+  e->conv_impl = impl;
+  return DCU_OK;
+}
+
+int64_t dcu_launch_count(const DcuEngine* e) { return e ? e->launches : 0; }
+
+int dcu_profile_enable(DcuEngine* e, int on) {
+  if (!e) return fail(DCU_ERR_INVALID, "null engine");
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaDeviceSynchronize());
+  for (auto& r : e->prof) { e->ev_pool.push_back(r.a); e->ev_pool.push_back(r.b); }
+  e->prof.clear();
+  e->profiling = on != 0;
+  return DCU_OK;
+}
+
+int dcu_profile_read(DcuEngine* e, int cls, double* total_ms, double* total_work, int64_t* n_launches) {
+  if (!e || !total_ms || !total_work || !n_launches) return fail(DCU_ERR_INVALID, "dcu_profile_read: bad argument");
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaDeviceSynchronize());
+  double ms = 0, work = 0; int64_t n = 0;
+  for (auto& r : e->prof) {
+    if (r.cls != cls) continue;
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t; work += r.work; ++n;
+  }
+  *total_ms = ms; *total_work = work; *n_launches = n;
+  return DCU_OK;
+}
+
+double dcu_detector_flops_per_frame(const DcuEngine* e) {
+  if (!e) return 0;
+  const double H = e->cfg.height, W = e->cfg.width;
+  double mac = 9.0 * 64 * H * W;                                                   // conv1a
+  mac += 9.0 * 64 * 64 * H * W;                                                    // conv1b
+  mac += 2 * 9.0 * 64 * 64 * (H / 2) * (W / 2);                                    // conv2a, 2b
+  mac += 9.0 * 64 * 128 * (H / 4) * (W / 4) + 9.0 * 128 * 128 * (H / 4) * (W / 4);   // conv3a, 3b
+  mac += 2 * 9.0 * 128 * 128 * (H / 8) * (W / 8);                                  // conv4a, 4b
+  mac += 2 * 9.0 * 128 * 256 * (H / 8) * (W / 8);                                  // convPa, convDa
+  mac += 256.0 * (65 + e->cfg.n_ids + 1) * (H / 8) * (W / 8);                      // convPb, convDb
+  return 2.0 * mac;
+}
+
+double dcu_refine_flops_per_patch(const DcuEngine*) {
+  double mac = 9.0 * 64 * 22 * 22 + 9.0 * 64 * 64 * 20 * 20 + 9.0 * 64 * 128 * 18 * 18 + 9.0 * 128 * 128 * 16 * 16;
+  mac += 2 * 9.0 * 128 * 128 * 8 * 8 + 2 * 9.0 * 128 * 128 * 16 * 16;
+  mac += 9.0 * 128 * 64 * 32 * 32 + 9.0 * 64 * 64 * 32 * 32 + 9.0 * 64 * 64 * 64 * 64 + 64.0 * 64 * 64;
+  return 2.0 * mac;
+}
+
+int dcu_detector_forward(DcuEngine* e, const uint8_t* frames_dev, int n, float* loc_dev, float* ids_dev, void* stream) {
+  if (!e || !frames_dev || !loc_dev || !ids_dev || n < 0) return fail(DCU_ERR_INVALID, "dcu_detector_forward: bad argument");
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int H = e->cfg.height, W = e->cfg.width, cells = (H / 8) * (W / 8);
+  for (int f0 = 0; f0 < n; f0 += e->mb2) {
+    const int m = std::min(e->mb2, n - f0);
+    int rc = detector_group(e, frames_dev + (size_t)f0 * H * W, nullptr, m, loc_dev + (size_t)f0 * 65 * cells,
+                            ids_dev + (size_t)f0 * (e->cfg.n_ids + 1) * cells, s);
+    if (rc) return rc;
+  }
+  return DCU_OK;
+}
+
+int dcu_detector_forward_f32(DcuEngine* e, const float* images_dev, int n, float* loc_dev, float* ids_dev, void* stream) {
+  if (!e || !images_dev || !loc_dev || !ids_dev || n < 0) return fail(DCU_ERR_INVALID, "dcu_detector_forward_f32: bad argument");
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int H = e->cfg.height, W = e->cfg.width, cells = (H / 8) * (W / 8);
+  for (int f0 = 0; f0 < n; f0 += e->mb2) {
+    const int m = std::min(e->mb2, n - f0);
+    int rc = detector_group(e, nullptr, images_dev + (size_t)f0 * H * W, m, loc_dev + (size_t)f0 * 65 * cells,
+                            ids_dev + (size_t)f0 * (e->cfg.n_ids + 1) * cells, s);
+    if (rc) return rc;
+  }
+  return DCU_OK;
+}
+
+int dcu_extract_patches(DcuEngine* e, const float* image_dev, const int32_t* xy_dev, int k, float* patches_dev, void* stream) {
+  if (!e || !image_dev || !xy_dev || !patches_dev || k < 0) return fail(DCU_ERR_INVALID, "dcu_extract_patches: bad argument");
+  CK(cudaSetDevice(e->cfg.device));
+  launch_extract_patches(image_dev, e->cfg.height, e->cfg.width, xy_dev, k, patches_dev, (cudaStream_t)stream);
+  e->launches++;
+  CK(cudaGetLastError());
+  return DCU_OK;
+}
+
+int dcu_decode_gather(DcuEngine* e, const float* loc_dev, const float* ids_dev, const uint8_t* frames_dev, int n,
+                      int dust_bin_ids, int append, int32_t* counts_dev, int32_t* offsets_dev, int32_t* total_dev,
+                      int32_t* kpts_dev, float* patches_dev, void* stream) {
+  if (!e || !loc_dev || !ids_dev || !counts_dev || !offsets_dev || !total_dev || !kpts_dev || n < 0)
+    return fail(DCU_ERR_INVALID, "dcu_decode_gather: bad argument");
+  if (patches_dev && !frames_dev) return fail(DCU_ERR_INVALID, "dcu_decode_gather: patches need frames");
+  if ((size_t)n * 8 > e->scan_state.bytes) return fail(DCU_ERR_INVALID, "dcu_decode_gather: n > max_batch");
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem = decode_smem_bytes((e->cfg.height / 8) * (e->cfg.width / 8));
+  if (smem > 200 * 1024) return fail(DCU_ERR_UNSUPPORTED, "frame too large for the single-CTA decode");
+  if (n == 0) { if (!append) CK(cudaMemsetAsync(total_dev, 0, 4, s)); return DCU_OK; }
+  return decode_group(e, loc_dev, ids_dev, frames_dev, n, dust_bin_ids, append, counts_dev, offsets_dev, total_dev,
+                      kpts_dev, patches_dev, s);
+}
+
+int dcu_refine_forward(DcuEngine* e, const float* patches_dev, const int32_t* xy_dev, int xy_stride, int p,
+                       int32_t* corners_dev, float* refined_dev, float* heat_dev, void* stream) {
+  if (!e || !patches_dev || !xy_dev || !refined_dev || p < 0 || xy_stride < 2)
+    return fail(DCU_ERR_INVALID, "dcu_refine_forward: bad argument");
+  if (!e->has_ref) return fail(DCU_ERR_INVALID, "engine was created without RefineNet weights");
+  if (p > e->cfg.max_patches) return fail(DCU_ERR_CAPACITY, "p > max_patches");
+  CK(cudaSetDevice(e->cfg.device));
+  return refine_run(e, patches_dev, xy_dev, xy_stride, p, corners_dev, refined_dev, heat_dev, (cudaStream_t)stream);
+}
+
+int dcu_infer_batch(DcuEngine* e, const uint8_t* frames_dev, int n, int dust_bin_ids, int use_refinenet,
+                    int32_t* counts_dev, int32_t* offsets_dev, int32_t* total_dev, int32_t* kpts_dev,
+                    float* refined_dev, void* stream) {
+  if (!e || !frames_dev || !counts_dev || !offsets_dev || !total_dev || !kpts_dev || n < 0)
+    return fail(DCU_ERR_INVALID, "dcu_infer_batch: bad argument");
+  if (n > e->cfg.max_batch) return fail(DCU_ERR_INVALID, "dcu_infer_batch: n > max_batch");
+  if (use_refinenet && (!e->has_ref || !refined_dev)) return fail(DCU_ERR_INVALID, "dcu_infer_batch: RefineNet not available");
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int H = e->cfg.height, W = e->cfg.width;
+  if (n == 0) { CK(cudaMemsetAsync(total_dev, 0, 4, s)); return DCU_OK; }
+  int rc;
+  for (int f0 = 0; f0 < n; f0 += e->mb2) {
+    const int m = std::min(e->mb2, n - f0);
+    const uint8_t* fr = frames_dev + (size_t)f0 * H * W;
+    if ((rc = detector_group(e, fr, nullptr, m, e->loc.as<float>(), e->ids.as<float>(), s))) return rc;
+    if ((rc = decode_group(e, e->loc.as<float>(), e->ids.as<float>(), fr, m, dust_bin_ids, f0 > 0, counts_dev + f0,
+                           offsets_dev + f0, total_dev, kpts_dev, use_refinenet ? e->patches.as<float>() : nullptr, s)))
+      return rc;
+  }
+  if (!use_refinenet) return DCU_OK;
+  CK(cudaMemcpyAsync(e->h_total, total_dev, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));   // corner count, as the reference's nonzero() does (model_utils.py:114)
+  const int total = std::min(e->h_total[0], e->cfg.max_patches);
+  return refine_run(e, e->patches.as<float>(), kpts_dev, 4, total, nullptr, refined_dev, nullptr, s);
+}
+
+int dcu_infer_batch_host(DcuEngine* e, const uint8_t* frames_host, int n, int dust_bin_ids, int use_refinenet,
+                         int32_t* counts_host, int32_t* offsets_host, int32_t* total_host, int32_t* kpts_host,
+                         float* refined_host, void* stream) {
+  if (!e || !frames_host || !counts_host || !offsets_host || !total_host || !kpts_host || n < 0)
+    return fail(DCU_ERR_INVALID, "dcu_infer_batch_host: bad argument");
+  if (n > e->cfg.max_batch) return fail(DCU_ERR_INVALID, "dcu_infer_batch_host: n > max_batch");
+  if (use_refinenet && !refined_host) return fail(DCU_ERR_INVALID, "dcu_infer_batch_host: refined_host is NULL");
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t fbytes = (size_t)n * e->cfg.height * e->cfg.width;
+  *total_host = 0;
+  if (n == 0) return DCU_OK;
+  // stage through the engine's pinned buffer unless the caller's memory is already pinned
+  const uint8_t* src = frames_host;
+  cudaPointerAttributes pa;
+  if (cudaPointerGetAttributes(&pa, frames_host) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+    cudaGetLastError();
+    std::memcpy(e->h_frames, frames_host, fbytes);
+    src = e->h_frames;
+  }
+  CK(cudaMemcpyAsync(e->frames.p, src, fbytes, cudaMemcpyHostToDevice, s));
+  int rc = dcu_infer_batch(e, e->frames.as<uint8_t>(), n, dust_bin_ids, use_refinenet, e->counts.as<int32_t>(),
+                           e->offsets.as<int32_t>(), e->total.as<int32_t>(), e->kpts.as<int32_t>(),
+                           e->refined.as<float>(), s);
+  if (rc) return rc;
+  int total;
+  if (use_refinenet) {
+    total = e->h_total[0];        // already fetched by dcu_infer_batch
+  } else {
+    CK(cudaMemcpyAsync(e->h_total, e->total.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    total = e->h_total[0];
+  }
+  const int kept = std::min(total, e->cfg.max_patches);
+  CK(cudaMemcpyAsync(e->h_counts, e->counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(e->h_offsets, e->offsets.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  if (kept > 0) {
+    CK(cudaMemcpyAsync(e->h_kpts, e->kpts.p, (size_t)kept * 16, cudaMemcpyDeviceToHost, s));
+    if (use_refinenet) CK(cudaMemcpyAsync(e->h_refined, e->refined.p, (size_t)kept * 8, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  std::memcpy(counts_host, e->h_counts, (size_t)n * 4);
+  std::memcpy(offsets_host, e->h_offsets, (size_t)n * 4);
+  if (kept > 0) {
+    std::memcpy(kpts_host, e->h_kpts, (size_t)kept * 16);
+    if (use_refinenet) std::memcpy(refined_host, e->h_refined, (size_t)kept * 8);
+  }
+  *total_host = total;
+  if (total > e->cfg.max_patches)
+    return fail(DCU_ERR_CAPACITY, "corner count " + std::to_string(total) + " exceeds max_patches " +
+                                      std::to_string(e->cfg.max_patches));
+  return DCU_OK;
+}
+
+int dcu_debug_conv_layer(DcuEngine* e, int net, int layer, int conv_impl, const float* in_dev, int n, int h, int w,
+                         float* out_dev, void* stream) {
+  if (!e || !in_dev || !out_dev || n < 1) return fail(DCU_ERR_INVALID, "dcu_debug_conv_layer: bad argument");
+  if (net == 1 && !e->has_ref) return fail(DCU_ERR_INVALID, "no RefineNet in this engine");
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const FirstLayer* fl = nullptr;
+  const Layer3x3* l = nullptr;
+  if (net == 0) {
+    if (layer == 0) fl = &e->det_first;
+    else if (layer >= 1 && layer <= 8) l = &e->det[layer - 1];
+  } else if (net == 1) {
+    if (layer == 0) fl = &e->ref_first;
+    else if (layer >= 1 && layer <= 10) l = &e->ref[layer - 1];
+  }
+  if (!fl && !l) return fail(DCU_ERR_INVALID, "dcu_debug_conv_layer: layer is not a 3x3 convolution");
+  const int cin = fl ? 1 : l->cin, cout = fl ? 64 : l->cout, pad = fl ? fl->pad : l->pad;
+  const int ho = h + 2 * pad - 2, wo = w + 2 * pad - 2;
+  int hf = ho, wf = wo;
+  if (l && l->pool) { hf = ho / 2; wf = wo / 2; }
+  if (l && l->ups) { hf = ho * 2; wf = wo * 2; }
+  DevBuf tin, tout;
+  CK(tin.alloc((size_t)n * cin * h * w * 4));
+  CK(tout.alloc((size_t)n * cout * hf * wf * 4));
+  int rc = DCU_OK;
+  if (fl) {
+    rc = run_first(e, *fl, nullptr, in_dev, tout.as<float>(), n, h, w, s);
+  } else {
+    launch_nchw_to_c4(in_dev, tin.as<float>(), n, cin, h, w, s);
+    rc = run_3x3(e, *l, conv_impl, tin.as<float>(), tout.as<float>(), n, h, w, nullptr, s);
+  }
+  if (rc == DCU_OK) {
+    launch_c4_to_nchw(tout.as<float>(), out_dev, n, cout, hf, wf, s);
+    cudaError_t ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess) rc = fail(DCU_ERR_CUDA, std::string("dcu_debug_conv_layer: ") + cudaGetErrorString(ce));
+  }
+  tin.release(); tout.release();
+  return rc;
+}
+
+}  // extern "C"

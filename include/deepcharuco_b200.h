@@ -1,0 +1,170 @@
+/*
+ * deepcharuco_b200 -- C ABI of the B200-native ChArUco keypoint inference engine.
+ *
+ * The reference (JunkyByte/deepcharuco) has no FFI: its boundary is the Python
+ * function surface of src/inference.py (load_models :73, infer_image :32,
+ * solve_pnp :15).  This header is what a ctypes binding of that surface calls
+ * instead of torch.nn modules; every entry point cites the reference code it
+ * replaces.  Plain pointers and sizes only -- no torch / C++ types.
+ *
+ * Conventions
+ *   - all `*_dev` pointers are CUDA device pointers on the engine's device;
+ *     `*_host` pointers are host memory (pinned or pageable);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     calls are asynchronous on that stream unless stated otherwise;
+ *   - return value: 0 = DCU_OK, negative = error; dcu_last_error() returns a
+ *     thread-local human-readable message for the last failing call;
+ *   - one engine serves one (device, stream) at a time; calls on one engine are
+ *     not re-entrant (the reference is single-threaded too, inference.py:32-70).
+ *
+ * Tensor layouts at the boundary are the reference's own:
+ *   frames  : uint8  [N][H][W]            grayscale (after cv2.cvtColor, inference.py:40)
+ *   loc     : float  [N][65][H/8][W/8]    NCHW, dcModel.forward output (net.py:74)
+ *   ids     : float  [N][n_ids+1][H/8][W/8]                            (net.py:77)
+ *   patches : float  [P][24][24]          extract_patches output (model_utils.py:19-36)
+ */
+#ifndef DEEPCHARUCO_B200_H
+#define DEEPCHARUCO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCU_OK             0
+#define DCU_ERR_INVALID   -1   /* bad argument (shape, NULL pointer, N > max_batch, ...) */
+#define DCU_ERR_CUDA      -2   /* a CUDA runtime / driver call failed */
+#define DCU_ERR_CAPACITY  -3   /* more corners than max_patches; results up to capacity are valid */
+#define DCU_ERR_UNSUPPORTED -4 /* e.g. not an sm_100 device */
+
+/* Which convolution implementation the engine uses for the 3x3 layers with Cin >= 64.
+ * Both are this library's own sm_100a kernels; neither is a fallback to a library. */
+#define DCU_CONV_FFMA   0      /* fp32 CUDA-core direct convolution (bring-up / strict-fp32 path) */
+#define DCU_CONV_TCGEN05 1     /* tcgen05.mma kind::tf32, 3-term hi/lo split, fp32 accumulate in TMEM */
+
+typedef struct DcuEngine DcuEngine;
+
+/* One convolution layer as the reference stores it (torch OIHW fp32), plus the eval-mode
+ * BatchNorm folded to a per-channel affine that is applied AFTER the fp32 accumulation:
+ *     y = relu(fma(acc + bias, alpha, beta))        (alpha == NULL: y = acc + bias, no ReLU)
+ * alpha = gamma / sqrt(var + eps), beta = bn_bias - mean * alpha, computed by the caller in fp32
+ * (net.py:60 `relu(bn(conv(x)))`, BatchNorm2d eps 1e-5).  All pointers are HOST pointers and are
+ * copied during dcu_create. */
+typedef struct DcuConvLayer {
+  const float* weight;   /* [cout][cin][k][k] */
+  const float* bias;     /* [cout] */
+  const float* alpha;    /* [cout] or NULL */
+  const float* beta;     /* [cout] or NULL */
+  int32_t cin, cout, ksize;
+} DcuConvLayer;
+
+typedef struct DcuConfig {
+  int32_t device;        /* CUDA device ordinal */
+  int32_t height, width; /* frame size, multiples of 8 (three 2x2 pools, net.py:62,65,68) */
+  int32_t n_ids;         /* board inner corners; ids head has n_ids+1 channels (net.py:48) */
+  int32_t max_batch;     /* frames per dcu_infer_* call (workspace is sized for this) */
+  int32_t max_patches;   /* corner capacity per call, summed over the batch */
+  int32_t conv_impl;     /* DCU_CONV_FFMA or DCU_CONV_TCGEN05 */
+  int32_t reserved;
+} DcuConfig;
+
+/* Replaces inference.load_models (inference.py:73-84): builds packed device weights + workspace.
+ * det_layers: 12 layers in net.py:22-48 order  (conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db);
+ * ref_layers: 12 layers in refinenet.py:22-47 order (conv1a,1b,2a,2b,3a,3b,4a,4b,5a,5b,Pa,Pb),
+ *             or NULL / n_ref == 0 for a detector-only engine (refinenet_ckpt=None). */
+int dcu_create(const DcuConfig* cfg, const DcuConvLayer* det_layers, int n_det,
+               const DcuConvLayer* ref_layers, int n_ref, DcuEngine** out);
+int dcu_destroy(DcuEngine* e);
+
+/* Replaces pre_bgr_image + dcModel.forward (model_utils.py:46-50, net.py:50-80) for N frames.
+ * frames_dev uint8 [N][H][W] -> loc_dev [N][65][H/8][W/8], ids_dev [N][n_ids+1][H/8][W/8]. */
+int dcu_detector_forward(DcuEngine* e, const uint8_t* frames_dev, int n,
+                         float* loc_dev, float* ids_dev, void* stream);
+
+/* Same from an already normalised fp32 image batch [N][H][W] -- the argument lModel.infer_image takes
+ * (net.py:127-128: `deepc.infer_image(img_gray)` with img_gray = (x-128)/255). */
+int dcu_detector_forward_f32(DcuEngine* e, const float* images_dev, int n,
+                             float* loc_dev, float* ids_dev, void* stream);
+
+/* Replaces extract_patches (model_utils.py:19-36) on its own: image_dev fp32 [H][W] (normalised),
+ * xy_dev [K][2] int32 -> patches_dev [K][24][24]; zeros outside the image. */
+int dcu_extract_patches(DcuEngine* e, const float* image_dev, const int32_t* xy_dev, int k,
+                        float* patches_dev, void* stream);
+
+/* Replaces pred_to_keypoints + extract_patches (model_utils.py:53-124, :19-36), batched, one kernel.
+ * Per frame f: counts_dev[f] = K_f and offsets_dev[f] = sum of K over earlier frames (assigned by
+ * frame index, deterministic).  Frame f owns rows [offsets_dev[f], +K_f) of
+ *     kpts_dev    [max_patches][4] int32 {x, y, id, cell}
+ *     patches_dev [max_patches][24][24] float   (may be NULL: raw decode only, no gather)
+ * sorted by (id, cell) -- the order inference.py:68-69 returns (stable sort by id of the row-major
+ * list; sort a frame's rows by `cell` to recover pred_to_keypoints order).  total_dev[0] = sum K_f;
+ * rows beyond max_patches are dropped and the caller sees total > max_patches (DCU_ERR_CAPACITY in
+ * the *_host entry point).  `append` != 0 continues numbering from the current *total_dev instead
+ * of 0 (used to decode a large batch in micro-batches). */
+int dcu_decode_gather(DcuEngine* e, const float* loc_dev, const float* ids_dev,
+                      const uint8_t* frames_dev, int n, int dust_bin_ids, int append,
+                      int32_t* counts_dev, int32_t* offsets_dev, int32_t* total_dev,
+                      int32_t* kpts_dev, float* patches_dev, void* stream);
+
+/* Replaces RefineNet.infer_patches (refinenet.py:85-115): patches [P][24][24] + integer keypoints
+ * xy_dev [P][xy_stride] int32 (x at +0, y at +1; xy_stride = 2 for a packed (K,2) array, 4 to pass
+ * kpts_dev rows directly)
+ * -> corners_dev [P][2] int32 (col, row) of the 64x64 arg-max (speedy_bargmax2d, model_utils.py:39-43)
+ *    refined_dev [P][2] float = (corners - 32) / 8 + (x, y).
+ * heat_dev (may be NULL) receives the [P][64][64] heat map, for stage-level tests only. */
+int dcu_refine_forward(DcuEngine* e, const float* patches_dev, const int32_t* xy_dev, int xy_stride, int p,
+                       int32_t* corners_dev, float* refined_dev, float* heat_dev, void* stream);
+
+/* Replaces the body of inference.infer_image (inference.py:41-60) for a batch resident in HBM:
+ * detector -> decode+gather -> RefineNet.  The call synchronises `stream` once internally (after the
+ * decode) to learn the corner count -- the reference does the same at model_utils.py:114.
+ * Outputs (device): counts_dev [N], offsets_dev [N], total_dev [1], kpts_dev [max_patches][4] int32
+ * {x, y, id, cell} and refined_dev [max_patches][2] float, both indexed by offsets_dev[f] + j.
+ * use_refinenet == 0 skips the RefineNet leg (refinenet=None, inference.py:54). */
+int dcu_infer_batch(DcuEngine* e, const uint8_t* frames_dev, int n, int dust_bin_ids, int use_refinenet,
+                    int32_t* counts_dev, int32_t* offsets_dev, int32_t* total_dev,
+                    int32_t* kpts_dev, float* refined_dev, void* stream);
+
+/* Same, end to end from HOST memory: H2D of the u8 frames, the pipeline, D2H of the packed result,
+ * stream-synchronised on return.  counts_host [N], offsets_host [N], kpts_host [max_patches][4],
+ * refined_host [max_patches][2]; *total_host = sum of counts.  Uses the engine's pinned staging. */
+int dcu_infer_batch_host(DcuEngine* e, const uint8_t* frames_host, int n, int dust_bin_ids, int use_refinenet,
+                         int32_t* counts_host, int32_t* offsets_host, int32_t* total_host,
+                         int32_t* kpts_host, float* refined_host, void* stream);
+
+/* Test hook: run ONE 3x3 conv(+BN+ReLU[+pool][+2x nearest up]) layer of either network on fp32 NCHW
+ * device tensors with the selected implementation (DCU_CONV_*), so each layer is checkable against
+ * the oracle in isolation.  net: 0 detector, 1 RefineNet; layer: index into the dcu_create tables.
+ * in_dev [n][cin][h][w] -> out_dev [n][cout][h'][w'] (pad/pool/upsample as the reference applies
+ * to that layer). */
+int dcu_debug_conv_layer(DcuEngine* e, int net, int layer, int conv_impl, const float* in_dev,
+                         int n, int h, int w, float* out_dev, void* stream);
+
+/* Select the 3x3 conv implementation after creation (DCU_CONV_*). */
+int dcu_set_conv_impl(DcuEngine* e, int conv_impl);
+
+/* Number of this library's kernels launched on behalf of `e` since creation (bench.py: gpu_launches). */
+int64_t dcu_launch_count(const DcuEngine* e);
+
+/* Per-kernel timing for bench.py's roofline figure.  While enabled, every launch made on behalf of `e`
+ * is bracketed by CUDA events on the launching stream.  dcu_profile_read synchronises, sums the event
+ * durations of kernel class `cls` since the last enable (0 = 3x3 conv [the dominant kernel], 1 = first-layer
+ * conv, 2 = 1x1 heads, 3 = decode+gather, 4 = RefineNet finalize) and returns them with the class's
+ * ALGORITHMIC work: flops (2*MAC) for classes 0-2, bytes for class 3. */
+int dcu_profile_enable(DcuEngine* e, int on);
+int dcu_profile_read(DcuEngine* e, int cls, double* total_ms, double* total_work, int64_t* n_launches);
+
+/* Algorithmic FLOPs (2*MAC) per frame of the detector and per patch of RefineNet for this engine's
+ * shapes (12.879 GFLOP / 320x240 frame, 0.8711 GFLOP / patch). */
+double dcu_detector_flops_per_frame(const DcuEngine* e);
+double dcu_refine_flops_per_patch(const DcuEngine* e);
+
+const char* dcu_last_error(void);
+const char* dcu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPCHARUCO_B200_H */

@@ -1,0 +1,100 @@
+"""CUDA engine vs. the committed reference outputs (tests/golden), through the public Python surface,
+which calls the C ABI (dcu_infer_batch_host).  Integer results bit-exact; refined corners within 1e-3 px."""
+import numpy as np
+import pytest
+
+import deepcharuco_b200 as dc
+from conftest import split_rows
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_refined(got, want, tol=1e-3):
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert np.array_equal(got[:, 2], want[:, 2])                       # ids bit-exact
+    assert np.abs(got[:, :2] - want[:, :2]).max() <= tol               # sub-pixel within 1e-3 px
+
+
+def test_sample_image_known_answer(models, golden_sample):
+    deepc, refinenet = models
+    g = golden_sample
+    kp, img = dc.infer_image(g["bgr"], 16, deepc, refinenet)
+    assert img is g["bgr"] or np.array_equal(img, g["bgr"])            # draw_pred=False returns the input image
+    assert kp.dtype == np.float64
+    _check_refined(kp, g["out_refined"])
+    raw, _ = dc.infer_image(g["bgr"], 16, deepc, None)
+    assert raw.dtype == np.int64 and np.array_equal(raw, g["out_raw"])   # integer pixels + ids: bit-exact
+
+
+def test_sample_image_pnp(models, golden_sample):
+    deepc, refinenet = models
+    g = golden_sample
+    kp, _ = dc.infer_image(g["bgr"], 16, deepc, refinenet)
+    ret, rvec, tvec = dc.solve_pnp(kp, 5, 5, 0.01, g["pnp_camera"], np.zeros(5))
+    assert ret and np.allclose(rvec, g["pnp_rvec"], atol=1e-6) and np.allclose(tvec, g["pnp_tvec"], atol=1e-6)
+    assert dc.solve_pnp(kp[:3], 5, 5, 0.01, g["pnp_camera"], np.zeros(5)) == (False, None, None)
+
+
+def test_synthetic_batch_matches_reference(models, golden_synth):
+    deepc, refinenet = models
+    g = golden_synth
+    res = dc.infer_batch(g["frames"], 16, deepc, refinenet)
+    want = split_rows(g["out_refined"], g["counts"])
+    assert [0 if r.size == 0 else r.shape[0] for r in res] == g["counts"].tolist()
+    for got, w in zip(res, want):
+        _check_refined(got, w)
+    raw = dc.infer_batch(g["frames"], 16, deepc, None)
+    for got, w in zip(raw, split_rows(g["out_raw"], g["counts"])):
+        assert got.dtype == np.int64 and np.array_equal(got, w)
+
+
+def test_batch_equals_single_frame_calls(models, golden_synth):
+    deepc, refinenet = models
+    frames = golden_synth["frames"][:5]
+    batch = dc.infer_batch(frames, 16, deepc, refinenet)
+    for f, b in zip(frames, batch):
+        one = dc.infer_batch(f[None], 16, deepc, refinenet)[0]
+        assert np.array_equal(one, b)
+
+
+def test_edge_cases(models, golden_edge):
+    deepc, refinenet = models
+    g = golden_edge
+    res = dc.infer_batch(g["frames"], 16, deepc, refinenet)
+    want = split_rows(g["out_refined"], g["counts"])
+    raw = dc.infer_batch(g["frames"], 16, deepc, None)
+    want_raw = split_rows(g["out_raw"], g["counts"])
+    for name, got, w, gr, wr in zip(g["names"].tolist(), res, want, raw, want_raw):
+        if len(w) == 0:
+            assert got.shape == (0,) and gr.shape == (0,), name       # np.array([]) for K == 0
+        else:
+            assert np.array_equal(gr, wr), name
+            _check_refined(got, w)
+
+
+def test_crowded_frame_exceeding_default_capacity(models, golden_edge):
+    """192 corners in one frame > a small max_patches: the wrapper grows the workspace instead of truncating."""
+    deepc, refinenet = models
+    g = golden_edge
+    i = g["names"].tolist().index("crowded")
+    ctx = deepc._ctx
+    ctx.close()
+    ctx.engine(240, 320, max_batch=1, max_patches=64)
+    got = dc.infer_batch(g["frames"][i:i + 1], 16, deepc, refinenet)[0]
+    assert got.shape == (192, 3)
+    ctx.close()
+
+
+def test_640x480(models, golden_640):
+    deepc, refinenet = models
+    g = golden_640
+    res = dc.infer_batch(g["frames"], 16, deepc, refinenet)
+    for got, w in zip(res, split_rows(g["out_refined"], g["counts"])):
+        _check_refined(got, w)
+
+
+def test_empty_batch_and_bad_shapes(models):
+    deepc, refinenet = models
+    assert dc.infer_batch(np.zeros((0, 240, 320), np.uint8), 16, deepc, refinenet) == []
+    with pytest.raises(Exception):
+        dc.infer_batch(np.zeros((1, 100, 101), np.uint8), 16, deepc, refinenet)     # not a multiple of 8

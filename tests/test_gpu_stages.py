@@ -1,0 +1,201 @@
+"""Stage-level parity through the C ABI: each stage of the CUDA path against the oracle / golden fixtures,
+fed with the REFERENCE's inputs for that stage so errors cannot compound."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import split_rows
+from deepcharuco_b200 import _native as N
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 2e-3      # |delta| on logits of magnitude ~1e2 for an fp32 path with a different summation order
+HEAT_TOL = 5e-5       # |delta| on the 64x64 heat map (range ~[0,1])
+
+
+def _cuda(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def engine(states):
+    e = N.Engine(states[0], states[1], 240, 320, 16, 0, max_batch=16, max_patches=4096)
+    yield e
+    e.close()
+
+
+def test_detector_logits(engine, golden_synth):
+    g = golden_synth
+    n = g["loc"].shape[0]
+    frames = _cuda(g["frames"][:n])
+    loc = torch.empty((n, 65, 30, 40), device="cuda")
+    ids = torch.empty((n, 17, 30, 40), device="cuda")
+    N.check(N.lib().dcu_detector_forward(engine.handle, frames.data_ptr(), n, loc.data_ptr(), ids.data_ptr(), None))
+    torch.cuda.synchronize()
+    dl = (loc.cpu().numpy() - g["loc"])
+    di = (ids.cpu().numpy() - g["ids"])
+    assert np.abs(dl).max() < LOGIT_TOL and np.abs(di).max() < LOGIT_TOL, (np.abs(dl).max(), np.abs(di).max())
+    assert np.array_equal(loc.cpu().numpy().argmax(1), g["loc"].argmax(1)) or np.abs(dl).max() < LOGIT_TOL
+    assert np.array_equal(ids.cpu().numpy().argmax(1), g["ids"].argmax(1))
+
+
+def test_detector_f32_entry_equals_u8_entry(engine, golden_synth):
+    f = golden_synth["frames"][:2]
+    x = _cuda(np.stack([oracle.pre_bgr_image(a)[0] for a in f]))
+    fr = _cuda(f)
+    out = [torch.empty((2, 65, 30, 40), device="cuda"), torch.empty((2, 17, 30, 40), device="cuda"),
+           torch.empty((2, 65, 30, 40), device="cuda"), torch.empty((2, 17, 30, 40), device="cuda")]
+    N.check(N.lib().dcu_detector_forward(engine.handle, fr.data_ptr(), 2, out[0].data_ptr(), out[1].data_ptr(), None))
+    N.check(N.lib().dcu_detector_forward_f32(engine.handle, x.data_ptr(), 2, out[2].data_ptr(), out[3].data_ptr(), None))
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], out[2]) and torch.equal(out[1], out[3])     # LUT == numpy normalisation, bit for bit
+
+
+def _decode(engine, loc, ids, frames, n, patches=True, append=0, total=None):
+    counts = torch.zeros(n, dtype=torch.int32, device="cuda")
+    offsets = torch.zeros(n, dtype=torch.int32, device="cuda")
+    total = torch.zeros(1, dtype=torch.int32, device="cuda") if total is None else total
+    kpts = torch.zeros((engine.max_patches, 4), dtype=torch.int32, device="cuda")
+    pt = torch.zeros((engine.max_patches, 24, 24), device="cuda") if patches else None
+    N.check(N.lib().dcu_decode_gather(engine.handle, loc.data_ptr(), ids.data_ptr(), frames.data_ptr() if frames is not None else None,
+                                      n, 16, append, counts.data_ptr(), offsets.data_ptr(), total.data_ptr(), kpts.data_ptr(),
+                                      pt.data_ptr() if patches else None, None))
+    torch.cuda.synchronize()
+    return counts.cpu().numpy(), offsets.cpu().numpy(), int(total.item()), kpts.cpu().numpy(), (pt.cpu().numpy() if patches else None)
+
+
+def test_decode_gather_bit_exact_on_reference_logits(engine, golden_synth):
+    g = golden_synth
+    n = g["loc"].shape[0]
+    counts, offsets, total, kpts, patches = _decode(engine, _cuda(g["loc"]), _cuda(g["ids"]), _cuda(g["frames"][:n]), n)
+    assert counts.tolist() == g["counts"][:n].tolist()
+    assert offsets.tolist() == np.concatenate([[0], np.cumsum(counts)[:-1]]).tolist() and total == counts.sum()
+    ref_kp = split_rows(g["kpts"], g["counts"])
+    ref_id = split_rows(g["ids_found"], g["counts"])
+    ref_pt = split_rows(g["patches"], g["counts"][:n])
+    for f in range(n):
+        rows = kpts[offsets[f]:offsets[f] + counts[f]]
+        # engine order = (id, cell); reference order = row-major: compare as the reference's stable sort by id
+        order = sorted(range(len(ref_id[f])), key=lambda i: ref_id[f][i])
+        assert np.array_equal(rows[:, :2], ref_kp[f][order]) and np.array_equal(rows[:, 2], ref_id[f][order])
+        # sorting the engine rows by cell restores pred_to_keypoints order
+        back = rows[np.argsort(rows[:, 3], kind="stable")]
+        assert np.array_equal(back[:, :2], ref_kp[f]) and np.array_equal(back[:, 2], ref_id[f])
+        assert np.array_equal(patches[offsets[f]:offsets[f] + counts[f]], ref_pt[f][order])     # fp32 patches bit-exact
+
+
+def test_decode_edge_cases(engine):
+    """ties -> first max; loc dustbin 64; ids dustbin; all-dustbin frame -> K = 0; append mode continues numbering."""
+    loc = np.full((3, 65, 30, 40), -1.0, np.float32)
+    ids = np.full((3, 17, 30, 40), -1.0, np.float32)
+    loc[:, 64] = 0.0                                   # everything dustbin by default
+    loc[0, 5, 2, 3] = loc[0, 9, 2, 3] = 3.0            # tie -> 5 -> x = 8*3+5, y = 8*2+0
+    ids[0, 2, 2, 3] = ids[0, 7, 2, 3] = 1.0            # tie -> id 2
+    loc[0, 63, 29, 39] = 1.0; ids[0, 0, 29, 39] = 1.0  # last cell, last pixel, id 0
+    loc[0, 10, 0, 0] = 1.0; ids[0, 16, 0, 0] = 5.0     # ids dustbin wins -> dropped
+    loc[2, 0, 7, 7] = 2.0; ids[2, 15, 7, 7] = 2.0
+    frames = np.zeros((3, 240, 320), np.uint8)
+    counts, offsets, total, kpts, _ = _decode(engine, _cuda(loc), _cuda(ids), _cuda(frames), 3)
+    assert counts.tolist() == [2, 0, 1] and offsets.tolist() == [0, 2, 2] and total == 3
+    assert kpts[0].tolist() == [319, 239, 0, 29 * 40 + 39]
+    assert kpts[1].tolist() == [29, 16, 2, 2 * 40 + 3]
+    assert kpts[2].tolist() == [56, 56, 15, 7 * 40 + 7]
+    want_k, want_i = oracle.pred_to_keypoints(loc[:1], ids[:1], 16)
+    assert sorted(map(tuple, kpts[:2, :2].tolist())) == sorted(map(tuple, want_k.tolist()))
+    # append: a second call continues after `total`
+    tot = torch.tensor([3], dtype=torch.int32, device="cuda")
+    c2, o2, t2, k2, _ = _decode(engine, _cuda(loc), _cuda(ids), _cuda(frames), 3, append=1, total=tot)
+    assert o2.tolist() == [3, 5, 5] and t2 == 6
+
+
+def test_patch_zero_padding_at_borders(engine):
+    """A corner at (0,0) / (319,239): the window hangs outside the frame and must read 0.0 (= gray 128 normalised)."""
+    loc = np.full((1, 65, 30, 40), -1.0, np.float32); loc[:, 64] = 0.0
+    ids = np.full((1, 17, 30, 40), -1.0, np.float32)
+    loc[0, 0, 0, 0] = 1.0; ids[0, 1, 0, 0] = 1.0
+    loc[0, 63, 29, 39] = 1.0; ids[0, 2, 29, 39] = 1.0
+    rng = np.random.default_rng(0)
+    frame = rng.integers(0, 256, (1, 240, 320)).astype(np.uint8)
+    counts, offsets, total, kpts, patches = _decode(engine, _cuda(loc), _cuda(ids), _cuda(frame), 1)
+    img = oracle.pre_bgr_image(frame[0])
+    want = oracle.extract_patches(img, kpts[:2, :2].astype(np.int64))
+    assert np.array_equal(patches[:2], want)
+    assert (want[0][:12, :] == 0).all() and (want[1][13:, :] == 0).all()
+
+
+def test_extract_patches_entry(engine, golden_synth):
+    g = golden_synth
+    img = oracle.pre_bgr_image(g["frames"][0])
+    kp = split_rows(g["kpts"], g["counts"])[0]
+    out = torch.empty((len(kp), 24, 24), device="cuda")
+    N.check(N.lib().dcu_extract_patches(engine.handle, _cuda(img).data_ptr(), _cuda(kp.astype(np.int32)).data_ptr(), len(kp), out.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), oracle.extract_patches(img, kp))
+
+
+def test_refinenet_on_reference_patches(engine, golden_synth):
+    g = golden_synth
+    p = g["patches"].shape[0]
+    kp = g["kpts"][:p].astype(np.int32)
+    corners = torch.empty((p, 2), dtype=torch.int32, device="cuda")
+    refined = torch.empty((p, 2), device="cuda")
+    heat = torch.empty((p, 64, 64), device="cuda")
+    N.check(N.lib().dcu_refine_forward(engine.handle, _cuda(g["patches"]).data_ptr(), _cuda(kp).data_ptr(), 2, p,
+                                       corners.data_ptr(), refined.data_ptr(), heat.data_ptr(), None))
+    torch.cuda.synchronize()
+    dh = np.abs(heat.cpu().numpy() - g["heat"]).max()
+    assert dh < HEAT_TOL, dh
+    got = corners.cpu().numpy()
+    want = g["corners"][:p]
+    bad = np.where((got != want).any(1))[0]
+    for j in bad:       # any flip must be a near-tie in the reference's own heat map
+        assert g["heat"][j].max() - g["heat"][j, got[j, 1], got[j, 0]] < HEAT_TOL
+    assert len(bad) <= 1
+    ref_refined = (want.astype(np.float32) - 32) / 8 + kp.astype(np.float32)
+    ok = np.setdiff1d(np.arange(p), bad)
+    assert np.array_equal(refined.cpu().numpy()[ok], ref_refined[ok])
+    # the engine's own arg-max is consistent with its own heat map (first max wins)
+    assert np.array_equal(got, oracle.bargmax2d(heat.cpu().numpy()))
+
+
+def _layer(engine, net, layer, impl, x):
+    n, c, h, w = x.shape
+    st_l = None
+    xin = _cuda(x)
+    # output shape comes from the oracle side; allocate generously
+    out = torch.empty(n * 512 * max(h, 64) * max(w, 64) // 4 + 1024, device="cuda")
+    N.check(N.lib().dcu_debug_conv_layer(engine.handle, net, layer, impl, xin.data_ptr(), n, h, w, out.data_ptr(), None))
+    return out
+
+
+@pytest.mark.parametrize("impl", [N.CONV_FFMA])
+def test_every_conv_layer_against_oracle(engine, states, golden_synth, impl):
+    """Feed each 3x3 layer the ORACLE's input activation and compare its output with the oracle's."""
+    g = golden_synth
+    sd, sr = states
+    x0 = torch.from_numpy(np.stack([oracle.pre_bgr_image(f) for f in g["frames"][:2]]))
+    _, _, fd = oracle.detector_forward(sd, x0, return_features=True)
+    det_chain = [("conv1a", x0), ("conv1b", fd["conv1a"]), ("conv2a", fd["conv1b"]), ("conv2b", fd["conv2a"]),
+                 ("conv3a", fd["conv2b"]), ("conv3b", fd["conv3a"]), ("conv4a", fd["conv3b"]), ("conv4b", fd["conv4a"])]
+    for li, (name, xin) in enumerate(det_chain):
+        want = fd[name].numpy()
+        got = _layer(engine, 0, li, impl, xin.numpy())[:want.size].view(*want.shape).cpu().numpy()
+        err = np.abs(got - want).max()
+        assert err < 1e-3 * max(1.0, np.abs(want).max()), (name, err)
+    want = torch.cat([fd["convPa"], fd["convDa"]], 1).numpy()
+    got = _layer(engine, 0, 8, impl, fd["conv4b"].numpy())[:want.size].view(*want.shape).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-3 * max(1.0, np.abs(want).max())
+
+    p0 = torch.from_numpy(g["patches"][:6])[:, None]
+    _, fr = oracle.refinenet_forward(sr, p0, return_features=True)
+    names = ["conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "conv4a", "conv4b", "conv5a", "conv5b", "convPa"]
+    xin = p0
+    for li, name in enumerate(names):
+        want = fr[name].numpy()
+        got = _layer(engine, 1, li, impl, xin.numpy())[:want.size].view(*want.shape).cpu().numpy()
+        err = np.abs(got - want).max()
+        assert err < 1e-4 * max(1.0, np.abs(want).max()), (name, err)
+        xin = fr[name]
