@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libdeepcharuco_b200.so")
 
 DCU_OK, DCU_ERR_INVALID, DCU_ERR_CUDA, DCU_ERR_CAPACITY, DCU_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 CONV_FFMA, CONV_TCGEN05 = 0, 1
-CONV_DEFAULT = CONV_FFMA   # flipped to CONV_TCGEN05 once that path is parity-green on the GPU
+CONV_DEFAULT = CONV_TCGEN05   # tcgen05 3xTF32 tensor-core path; CONV_FFMA is the strict-fp32 CUDA-core path
 
 EXPORTS = [
     "dcu_create", "dcu_destroy", "dcu_detector_forward", "dcu_detector_forward_f32", "dcu_extract_patches",
@@ -138,7 +138,7 @@ class Engine:
     """One C engine: fixed (device, H, W, n_ids), workspace for max_batch frames / max_patches corners."""
 
     def __init__(self, state_det, state_ref, height, width, n_ids=16, device=0, max_batch=1, max_patches=None,
-                 conv_impl=CONV_FFMA):
+                 conv_impl=CONV_DEFAULT):
         L = lib()
         if max_patches is None:
             max_patches = max(256, 64 * max_batch)

@@ -200,6 +200,10 @@ def infer_batch(frames, dust_bin_ids: int, deepc: DeepcHandle, refinenet: Option
         frames = np.stack([cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in frames])
     assert frames.ndim == 3 and frames.dtype == np.uint8, "frames must be (N,H,W) uint8"
     n, H, W = frames.shape
+    if H % 8 or W % 8:
+        raise ValueError(f"frame size {W}x{H} must be a multiple of 8 (three 2x2 pools, net.py:62,65,68)")
+    if n == 0:
+        return []
     ctx = deepc._ctx
     eng = ctx.engine(H, W, max_batch=n)
     while True:

@@ -69,6 +69,16 @@ def models():
     return dc.load_models(dc.DEFAULT_DEEPC, dc.DEFAULT_REFINENET, n_ids=16, device="cuda")
 
 
+@pytest.fixture(scope="session")
+def models_ffma():
+    """Same, pinned to the fp32 CUDA-core convolution kernels (DCU_CONV_FFMA)."""
+    import deepcharuco_b200 as dc
+    from deepcharuco_b200 import _native as N
+    deepc, refinenet = dc.load_models(dc.DEFAULT_DEEPC, dc.DEFAULT_REFINENET, n_ids=16, device="cuda")
+    deepc._ctx.set_conv_impl(N.CONV_FFMA)
+    return deepc, refinenet
+
+
 def split_rows(rows, counts):
     out, o = [], 0
     for c in counts.tolist():

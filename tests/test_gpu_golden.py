@@ -48,6 +48,17 @@ def test_synthetic_batch_matches_reference(models, golden_synth):
         assert got.dtype == np.int64 and np.array_equal(got, w)
 
 
+def test_fp32_cuda_core_path_matches_reference_too(models_ffma, golden_sample, golden_synth):
+    deepc, refinenet = models_ffma
+    kp, _ = dc.infer_image(golden_sample["bgr"], 16, deepc, refinenet)
+    _check_refined(kp, golden_sample["out_refined"])
+    g = golden_synth
+    for got, w in zip(dc.infer_batch(g["frames"], 16, deepc, refinenet), split_rows(g["out_refined"], g["counts"])):
+        _check_refined(got, w)
+    for got, w in zip(dc.infer_batch(g["frames"], 16, deepc, None), split_rows(g["out_raw"], g["counts"])):
+        assert np.array_equal(got, w)
+
+
 def test_batch_equals_single_frame_calls(models, golden_synth):
     deepc, refinenet = models
     frames = golden_synth["frames"][:5]

@@ -131,7 +131,8 @@ def test_extract_patches_entry(engine, golden_synth):
     img = oracle.pre_bgr_image(g["frames"][0])
     kp = split_rows(g["kpts"], g["counts"])[0]
     out = torch.empty((len(kp), 24, 24), device="cuda")
-    N.check(N.lib().dcu_extract_patches(engine.handle, _cuda(img).data_ptr(), _cuda(kp.astype(np.int32)).data_ptr(), len(kp), out.data_ptr(), None))
+    d_img, d_kp = _cuda(img), _cuda(kp.astype(np.int32))       # keep the device tensors alive across the async call
+    N.check(N.lib().dcu_extract_patches(engine.handle, d_img.data_ptr(), d_kp.data_ptr(), len(kp), out.data_ptr(), None))
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), oracle.extract_patches(img, kp))
 
@@ -143,7 +144,8 @@ def test_refinenet_on_reference_patches(engine, golden_synth):
     corners = torch.empty((p, 2), dtype=torch.int32, device="cuda")
     refined = torch.empty((p, 2), device="cuda")
     heat = torch.empty((p, 64, 64), device="cuda")
-    N.check(N.lib().dcu_refine_forward(engine.handle, _cuda(g["patches"]).data_ptr(), _cuda(kp).data_ptr(), 2, p,
+    d_patches, d_kp = _cuda(g["patches"]), _cuda(kp)            # keep alive: the call is asynchronous
+    N.check(N.lib().dcu_refine_forward(engine.handle, d_patches.data_ptr(), d_kp.data_ptr(), 2, p,
                                        corners.data_ptr(), refined.data_ptr(), heat.data_ptr(), None))
     torch.cuda.synchronize()
     dh = np.abs(heat.cpu().numpy() - g["heat"]).max()
@@ -161,17 +163,16 @@ def test_refinenet_on_reference_patches(engine, golden_synth):
     assert np.array_equal(got, oracle.bargmax2d(heat.cpu().numpy()))
 
 
-def _layer(engine, net, layer, impl, x):
+def _layer(engine, net, layer, impl, x, out_shape):
     n, c, h, w = x.shape
-    st_l = None
     xin = _cuda(x)
-    # output shape comes from the oracle side; allocate generously
-    out = torch.empty(n * 512 * max(h, 64) * max(w, 64) // 4 + 1024, device="cuda")
+    out = torch.full(tuple(out_shape), float("nan"), device="cuda")
     N.check(N.lib().dcu_debug_conv_layer(engine.handle, net, layer, impl, xin.data_ptr(), n, h, w, out.data_ptr(), None))
-    return out
+    torch.cuda.synchronize()      # (the entry point synchronises too; xin must outlive the kernels)
+    return out.cpu().numpy()
 
 
-@pytest.mark.parametrize("impl", [N.CONV_FFMA])
+@pytest.mark.parametrize("impl", [N.CONV_FFMA, N.CONV_TCGEN05])
 def test_every_conv_layer_against_oracle(engine, states, golden_synth, impl):
     """Feed each 3x3 layer the ORACLE's input activation and compare its output with the oracle's."""
     g = golden_synth
@@ -182,12 +183,12 @@ def test_every_conv_layer_against_oracle(engine, states, golden_synth, impl):
                  ("conv3a", fd["conv2b"]), ("conv3b", fd["conv3a"]), ("conv4a", fd["conv3b"]), ("conv4b", fd["conv4a"])]
     for li, (name, xin) in enumerate(det_chain):
         want = fd[name].numpy()
-        got = _layer(engine, 0, li, impl, xin.numpy())[:want.size].view(*want.shape).cpu().numpy()
+        got = _layer(engine, 0, li, N.CONV_FFMA if li == 0 else impl, xin.numpy(), want.shape)
         err = np.abs(got - want).max()
-        assert err < 1e-3 * max(1.0, np.abs(want).max()), (name, err)
+        assert err < 1e-4 * max(1.0, np.abs(want).max()), (name, err)
     want = torch.cat([fd["convPa"], fd["convDa"]], 1).numpy()
-    got = _layer(engine, 0, 8, impl, fd["conv4b"].numpy())[:want.size].view(*want.shape).cpu().numpy()
-    assert np.abs(got - want).max() < 1e-3 * max(1.0, np.abs(want).max())
+    got = _layer(engine, 0, 8, impl, fd["conv4b"].numpy(), want.shape)
+    assert np.abs(got - want).max() < 1e-4 * max(1.0, np.abs(want).max())
 
     p0 = torch.from_numpy(g["patches"][:6])[:, None]
     _, fr = oracle.refinenet_forward(sr, p0, return_features=True)
@@ -195,7 +196,7 @@ def test_every_conv_layer_against_oracle(engine, states, golden_synth, impl):
     xin = p0
     for li, name in enumerate(names):
         want = fr[name].numpy()
-        got = _layer(engine, 1, li, impl, xin.numpy())[:want.size].view(*want.shape).cpu().numpy()
+        got = _layer(engine, 1, li, N.CONV_FFMA if li == 0 else impl, xin.numpy(), want.shape)
         err = np.abs(got - want).max()
         assert err < 1e-4 * max(1.0, np.abs(want).max()), (name, err)
         xin = fr[name]

@@ -1,0 +1,89 @@
+"""The tcgen05 (3xTF32) convolution path: per layer against the fp32 CUDA-core kernel and the oracle, then the
+whole pipeline against the golden fixtures and the oracle.  Runs last (a kernel fault poisons the CUDA context)."""
+import numpy as np
+import pytest
+import torch
+
+import deepcharuco_b200 as dc
+import oracle
+import parity
+from conftest import split_rows
+from deepcharuco_b200 import _native as N, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine(states):
+    e = N.Engine(states[0], states[1], 240, 320, 16, 0, max_batch=16, max_patches=4096)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def tc_models():
+    deepc, refinenet = dc.load_models(dc.DEFAULT_DEEPC, dc.DEFAULT_REFINENET, n_ids=16, device="cuda")
+    deepc._ctx.set_conv_impl(N.CONV_TCGEN05)
+    return deepc, refinenet
+
+
+SHAPES = [  # net, layer, cin, h, w, cout, out_h, out_w
+    (0, 1, 64, 240, 320, 64, 120, 160), (0, 2, 64, 120, 160, 64, 120, 160), (0, 4, 64, 60, 80, 128, 60, 80),
+    (0, 5, 128, 60, 80, 128, 30, 40), (0, 6, 128, 30, 40, 128, 30, 40), (0, 8, 128, 30, 40, 512, 30, 40),
+    (1, 1, 64, 22, 22, 64, 20, 20), (1, 2, 64, 20, 20, 128, 18, 18), (1, 3, 128, 18, 18, 128, 8, 8),
+    (1, 4, 128, 8, 8, 128, 8, 8), (1, 5, 128, 8, 8, 128, 16, 16), (1, 6, 128, 16, 16, 128, 16, 16),
+    (1, 8, 128, 32, 32, 64, 32, 32), (1, 9, 64, 32, 32, 64, 64, 64), (1, 10, 64, 64, 64, 64, 64, 64),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_layer_tcgen05_matches_fp32_kernel(engine, shape):
+    net, layer, cin, h, w, cout, oh, ow = shape
+    rng = np.random.default_rng(layer * 7 + net)
+    n = 3
+    x = torch.from_numpy(np.maximum(rng.standard_normal((n, cin, h, w)).astype(np.float32), 0)).cuda()
+    outs = []
+    for impl in (N.CONV_FFMA, N.CONV_TCGEN05):
+        out = torch.full((n, cout, oh, ow), float("nan"), device="cuda")
+        N.check(N.lib().dcu_debug_conv_layer(engine.handle, net, layer, impl, x.data_ptr(), n, h, w, out.data_ptr(), None))
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+    a, b = outs
+    assert not np.isnan(b).any()
+    # 3xTF32 keeps ~22 mantissa bits per operand: agreement with the fp32 FMA kernel at fp32-noise level
+    assert np.abs(a - b).max() <= 2e-5 * max(1.0, np.abs(a).max()), np.abs(a - b).max()
+
+
+def test_pipeline_golden_tcgen05(tc_models, golden_sample, golden_synth):
+    deepc, refinenet = tc_models
+    kp, _ = dc.infer_image(golden_sample["bgr"], 16, deepc, refinenet)
+    assert np.array_equal(kp[:, 2], golden_sample["out_refined"][:, 2])
+    assert np.abs(kp[:, :2] - golden_sample["out_refined"][:, :2]).max() <= 1e-3
+    raw, _ = dc.infer_image(golden_sample["bgr"], 16, deepc, None)
+    assert np.array_equal(raw, golden_sample["out_raw"])
+    g = golden_synth
+    res = dc.infer_batch(g["frames"], 16, deepc, refinenet)
+    for got, w in zip(res, split_rows(g["out_refined"], g["counts"])):
+        assert got.shape == w.shape and np.array_equal(got[:, 2], w[:, 2])
+        assert np.abs(got[:, :2] - w[:, :2]).max() <= 1e-3
+
+
+def test_parity_tcgen05_vs_oracle(tc_models, states):
+    deepc, refinenet = tc_models
+    frames = synth.make_frames(48, 240, 320, seed=1)
+    refined = dc.infer_batch(frames, 16, deepc, refinenet)
+    raw = dc.infer_batch(frames, 16, deepc, None)
+    tot = parity.summarise([parity.compare_frame(states, f, r, w) for f, r, w in zip(frames, refined, raw)])
+    print("PARITY tcgen05 320x240 seed1:", tot)
+    parity.assert_parity(tot)
+    assert tot["heat_flip"] + tot["raw_px"] <= max(2, tot["K"] // 200), tot
+
+
+def test_tcgen05_deterministic_and_batch_invariant(tc_models):
+    deepc, refinenet = tc_models
+    frames = synth.tile_frames(synth.make_frames(16, 240, 320, seed=2), 64)
+    a = dc.infer_batch(frames, 16, deepc, refinenet)
+    b = dc.infer_batch(frames, 16, deepc, refinenet)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    one = dc.infer_batch(frames[5:6], 16, deepc, refinenet)[0]
+    assert np.array_equal(one, a[5])

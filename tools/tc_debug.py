@@ -1,0 +1,74 @@
+"""On-GPU diagnostic for the tcgen05 conv kernel: every 3x3 layer shape, tcgen05 vs the fp32 CUDA-core kernel
+(same input), printing error statistics instead of asserting.  Run under `timeout` on the GPU box:
+
+    python tools/tc_debug.py [layer-filter]
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+from deepcharuco_b200 import _native as N, weights_io as W  # noqa: E402
+
+sd, sr = W.load_state(W.DEFAULT_DEEPC), W.load_state(W.DEFAULT_REFINENET)
+eng = N.Engine(sd, sr, 240, 320, 16, 0, max_batch=8, max_patches=1024)
+L = N.lib()
+rng = np.random.default_rng(0)
+
+# (net, layer, cin, h, w, cout, out_h, out_w, name)
+CASES = [
+    (0, 1, 64, 240, 320, 64, 120, 160, "det conv1b +pool"),
+    (0, 2, 64, 120, 160, 64, 120, 160, "det conv2a"),
+    (0, 3, 64, 120, 160, 64, 60, 80, "det conv2b +pool"),
+    (0, 4, 64, 60, 80, 128, 60, 80, "det conv3a"),
+    (0, 5, 128, 60, 80, 128, 30, 40, "det conv3b +pool"),
+    (0, 6, 128, 30, 40, 128, 30, 40, "det conv4a"),
+    (0, 8, 128, 30, 40, 512, 30, 40, "det convPa|Da"),
+    (1, 1, 64, 22, 22, 64, 20, 20, "ref conv1b valid"),
+    (1, 2, 64, 20, 20, 128, 18, 18, "ref conv2a valid"),
+    (1, 3, 128, 18, 18, 128, 8, 8, "ref conv2b valid +pool"),
+    (1, 4, 128, 8, 8, 128, 8, 8, "ref conv3a"),
+    (1, 5, 128, 8, 8, 128, 16, 16, "ref conv3b +up"),
+    (1, 6, 128, 16, 16, 128, 16, 16, "ref conv4a"),
+    (1, 8, 128, 32, 32, 64, 32, 32, "ref conv5a"),
+    (1, 9, 64, 32, 32, 64, 64, 64, "ref conv5b +up"),
+    (1, 10, 64, 64, 64, 64, 64, 64, "ref convPa"),
+]
+flt = sys.argv[1] if len(sys.argv) > 1 else ""
+ok_all = True
+for net, layer, cin, h, w, cout, oh, ow, name in CASES:
+    if flt and flt not in name:
+        continue
+    n = 3
+    x = torch.from_numpy(np.maximum(rng.standard_normal((n, cin, h, w)).astype(np.float32), 0)).cuda()   # post-ReLU-like
+    outs = []
+    for impl in (N.CONV_FFMA, N.CONV_TCGEN05):
+        out = torch.full((n, cout, oh, ow), float("nan"), device="cuda")
+        rc = L.dcu_debug_conv_layer(eng.handle, net, layer, impl, x.data_ptr(), n, h, w, out.data_ptr(), None)
+        if rc != 0:
+            print(f"{name:26s} impl={impl} rc={rc} {L.dcu_last_error().decode()}")
+            outs.append(None)
+            continue
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+    if outs[0] is None or outs[1] is None:
+        ok_all = False
+        continue
+    a, b = outs
+    d = np.abs(a - b)
+    scale = max(1.0, float(np.abs(a).max()))
+    nan = int(np.isnan(b).sum())
+    bad = d > 1e-4 * scale
+    msg = f"{name:26s} max|ffma|={np.abs(a).max():9.3f} max|d|={np.nanmax(d):.3e} rel={np.nanmax(d)/scale:.2e} nan={nan} bad={int(bad.sum())}/{d.size}"
+    if nan or bad.any():
+        ok_all = False
+        idx = np.argwhere(bad | np.isnan(b))[:6]
+        msg += " first_bad=" + str(idx.tolist())
+        # which output channels / rows / cols are affected
+        bb = bad | np.isnan(b)
+        msg += f" bad_ch={np.unique(np.where(bb)[1])[:12].tolist()} bad_rows={np.unique(np.where(bb)[2])[:12].tolist()} bad_cols={np.unique(np.where(bb)[3])[:12].tolist()}"
+    print(msg, flush=True)
+print("TC_DEBUG", "ALL OK" if ok_all else "MISMATCH")
