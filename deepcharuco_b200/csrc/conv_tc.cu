@@ -22,7 +22,7 @@
 //
 // Roles (384 threads, one persistent CTA per SM, TMEM 512 columns = 2 accumulator buffers):
 //   warp 0      TMA producer for activation halo chunks          (a_empty -> a_full)
-//   warp 1      single-thread tcgen05.mma issuer                 (a_ready, b_full -> commits)
+//   warp 1      tcgen05.mma issuer: warp-uniform loop, one elected lane issues (a_ready, b_full -> commits)
 //   warp 2      TMEM alloc/dealloc + bulk-copy producer for weight blocks (b_empty -> b_full)
 //   warps 4-7   epilogue: tcgen05.ld -> bias/BN/ReLU -> pool | upsample | head -> global   (acc_full -> acc_empty)
 //   warps 8-11  hi/lo splitter: raw fp32 halo -> tf32 hi (in place) + tf32 lo  (a_full -> a_ready)
@@ -120,6 +120,31 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// 64-bit descriptors passed as two 32-bit halves: only the low word (start address field) changes between MMAs
+__device__ __forceinline__ void umma_tf32_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -193,7 +218,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
   uint64_t* acc_empty = acc_full + 2;              // [2] (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (keeps role code on the uniform datapath)
+  const int lane = threadIdx.x & 31;
   const int chunks = p.cin >> 4;
   const int halo_px = g.halo_w * g.halo_h;
   const uint32_t plane = (uint32_t)halo_px * 16u;
@@ -246,49 +272,63 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
         if (++st == B_STAGES) { st = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ================= MMA issuer =================
+  } else if (warp == 1) {
+    // ================= MMA issuer: whole warp runs the (uniform) loop, one elected lane issues =================
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | (8u << 24);
-    const uint32_t sbo_a = (uint32_t)g.halo_w * 16u;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    // descriptor words (cute::UMMA::SmemDescriptor): lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version(1)<<14
+    const uint32_t a_desc_hi = (uint32_t)g.halo_w | (1u << 14);                 // SBO = halo_w * 16 B
+    const uint32_t a_desc_lo0 = ((uint32_t)halo_px << 16);                      // LBO = plane = halo_px * 16 B
+    constexpr uint32_t b_desc_hi = 8u | (1u << 14);                             // SBO = 128 B
+    constexpr uint32_t b_desc_lo0 = ((uint32_t)NT << 16);                       // LBO = NT * 16 B
+    const uint32_t a_base0 = smem_u32(a_smem) >> 4, b_base0 = smem_u32(b_smem) >> 4;   // 16-byte units from here on
+    const uint32_t ks_off = 2u * (uint32_t)halo_px;                             // two channel-group planes per k-step
+    uint32_t mt_off[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int tri = mt / g.tc, tci = mt - tri * g.tc;
+      mt_off[mt] = (uint32_t)(tri * 16 * g.halo_w + tci * 8);
+    }
     int sa = 0, sb = 0, buf = 0; uint32_t pha = 0, phb = 0, phc = 0;
     for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       mbar_wait(&acc_empty[buf], phc ^ 1u);
       tc_fence_after();
+      const uint32_t d0 = tmem_u + (uint32_t)(buf * (MT * NT));
       for (int q = 0; q < chunks; ++q) {
         mbar_wait(&a_ready[sa], pha);
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(a_smem + (size_t)sa * Cfg::A_STAGE_BYTES);
-        const uint32_t a_lo = a_hi + (uint32_t)Cfg::A_HALF_BYTES;
+        const uint32_t a_hi = a_desc_lo0 + a_base0 + (uint32_t)sa * (Cfg::A_STAGE_BYTES >> 4);
+#pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&b_full[sb], phb);
           tc_fence_after();
           const int ky = tap / 3, kx = tap - 3 * ky;
-          const uint32_t b_hi = smem_u32(b_smem + (size_t)sb * Cfg::B_BLOCK_BYTES);
-          const uint32_t b_lo = b_hi + 4u * NT * 16u;
+          const uint32_t a_tap = a_hi + (uint32_t)(ky * g.halo_w + kx);
+          const uint32_t b_hi = b_desc_lo0 + b_base0 + (uint32_t)sb * (Cfg::B_BLOCK_BYTES >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const int tri = mt / g.tc, tci = mt - tri * g.tc;
-            const uint32_t px_off = (uint32_t)((tri * 16 + ky) * g.halo_w + tci * 8 + kx) * 16u;
-            const uint32_t d = tmem_base + (uint32_t)(buf * (MT * NT) + mt * NT);
+            for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t da_hi = make_desc(a_hi + 2u * ks * plane + px_off, plane, sbo_a);
-              const uint64_t da_lo = make_desc(a_lo + 2u * ks * plane + px_off, plane, sbo_a);
-              const uint64_t db_hi = make_desc(b_hi + 2u * ks * NT * 16u, NT * 16u, 128u);
-              const uint64_t db_lo = make_desc(b_lo + 2u * ks * NT * 16u, NT * 16u, 128u);
-              const uint32_t first = (q | tap | ks) ? 1u : 0u;
-              umma_tf32(d, da_lo, db_hi, IDESC, first);   // small terms first
-              umma_tf32(d, da_hi, db_lo, IDESC, 1u);
-              umma_tf32(d, da_hi, db_hi, IDESC, 1u);
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint32_t da_hi = a_tap + mt_off[mt] + ks * ks_off;
+                const uint32_t da_lo = da_hi + (uint32_t)(Cfg::A_HALF_BYTES >> 4);
+                const uint32_t db_hi = b_hi + ks * (2u * NT);
+                const uint32_t db_lo = db_hi + 4u * NT;
+                const uint32_t d = d0 + (uint32_t)(mt * NT);
+                umma_tf32_w(d, da_lo, a_desc_hi, db_hi, b_desc_hi, IDESC, (q | tap | ks) ? 1u : 0u);   // small terms first
+                umma_tf32_w(d, da_hi, a_desc_hi, db_lo, b_desc_hi, IDESC, 1u);
+                umma_tf32_w(d, da_hi, a_desc_hi, db_hi, b_desc_hi, IDESC, 1u);
+              }
             }
+            umma_commit(&b_empty[sb]);
+            if (tap == 8) umma_commit(&a_empty[sa]);
+            if (tap == 8 && q == chunks - 1) umma_commit(&acc_full[buf]);
           }
-          umma_commit(&b_empty[sb]);
+          __syncwarp();
           if (++sb == B_STAGES) { sb = 0; phb ^= 1u; }
         }
-        umma_commit(&a_empty[sa]);
         if (++sa == Cfg::A_STAGES) { sa = 0; pha ^= 1u; }
       }
-      umma_commit(&acc_full[buf]);
       if (++buf == 2) { buf = 0; phc ^= 1u; }
     }
   } else if (warp >= 8) {
@@ -301,13 +341,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
         mbar_wait(&a_full[st], ph);
         float4* raw = reinterpret_cast<float4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES + Cfg::A_HALF_BYTES);
-        for (int i = tid; i < n4; i += 128) {
-          const float4 v = raw[i];
-          float4 h, l;
-          h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
-          l.x = tf32_rn(v.x - h.x); l.y = tf32_rn(v.y - h.y); l.z = tf32_rn(v.z - h.z); l.w = tf32_rn(v.w - h.w);
-          raw[i] = h;
-          lo[i] = l;
+        // 4 independent 16-byte loads in flight per thread, then the 8 stores
+        for (int i0 = tid; i0 < n4; i0 += 4 * 128) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 128;
+            v[u] = (i < n4) ? raw[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 128;
+            if (i < n4) {
+              float4 h, l;
+              h.x = tf32_rn(v[u].x); h.y = tf32_rn(v[u].y); h.z = tf32_rn(v[u].z); h.w = tf32_rn(v[u].w);
+              l.x = tf32_rn(v[u].x - h.x); l.y = tf32_rn(v[u].y - h.y); l.z = tf32_rn(v[u].z - h.z); l.w = tf32_rn(v[u].w - h.w);
+              raw[i] = h;
+              lo[i] = l;
+            }
+          }
         }
         fence_proxy_async();               // generic-proxy writes -> visible to the tensor-core (async) proxy
         mbar_arrive(&a_ready[st]);
@@ -339,8 +391,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
           tmem_ld32(tmem_base + lane_addr + (uint32_t)(buf * (MT * NT) + mt * NT + cc * 32), v);
           const int ch0 = ch_base + cc * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = fmaxf(fmaf(v[j] + prm[ch0 + j], prm[512 + ch0 + j], prm[1024 + ch0 + j]), 0.0f);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bi = *reinterpret_cast<const float4*>(&prm[ch0 + j]);
+            const float4 al = *reinterpret_cast<const float4*>(&prm[512 + ch0 + j]);
+            const float4 be = *reinterpret_cast<const float4*>(&prm[1024 + ch0 + j]);
+            v[j + 0] = fmaxf(fmaf(v[j + 0] + bi.x, al.x, be.x), 0.0f);
+            v[j + 1] = fmaxf(fmaf(v[j + 1] + bi.y, al.y, be.y), 0.0f);
+            v[j + 2] = fmaxf(fmaf(v[j + 2] + bi.z, al.z, be.z), 0.0f);
+            v[j + 3] = fmaxf(fmaf(v[j + 3] + bi.w, al.w, be.w), 0.0f);
+          }
           if (p.head_w != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) head_sum = fmaf(v[j], __ldg(p.head_w + cc * 32 + j), head_sum);

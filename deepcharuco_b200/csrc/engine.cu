@@ -174,7 +174,7 @@ struct DcuEngine {
   DevBuf ref_head_w; float ref_head_b = 0.f;
 
   DevBuf lut;                   // [256] (x-128)/255
-  int mb1 = 4, mb2 = 32, rp = 64;   // micro-batch sizes: full-res layers, low-res layers, RefineNet patches
+  int mb1 = 32, mb2 = 256, rp = 1024;   // micro-batch sizes: full-res layers, low-res layers, RefineNet patches
   DevBuf act[2];                // ping-pong activation buffers
   DevBuf stage2_in;             // conv2b output for mb2 frames (input of conv3a)
   DevBuf heads;                 // (Pa|Da) output for mb2 frames
@@ -475,8 +475,13 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   // workspace
   const int H = cfg->height, W = cfg->width;
   const double area = (double)H * W / (320.0 * 240.0);
-  e->mb1 = std::max(1, (int)std::floor(4.0 / area + 1e-9));
-  e->mb2 = std::max(e->mb1, (int)std::floor(32.0 / area + 1e-9));
+  // Sized for wave efficiency, not L2 residency: at the tensor-bound rate the activation traffic is a few hundred
+  // GB/s, far below HBM bandwidth, while a launch with few tiles leaves most of the 148 SMs idle in its last wave.
+  e->mb1 = std::max(1, (int)std::floor(32.0 / area + 1e-9));
+  e->mb2 = std::max(e->mb1, (int)std::floor(256.0 / area + 1e-9));
+  e->mb1 = std::min(e->mb1, std::max(1, cfg->max_batch));
+  e->mb2 = std::min(e->mb2, std::max(e->mb1, cfg->max_batch));
+  e->rp = std::min(1024, std::max(64, cfg->max_patches));
   if (const char* v = getenv("DCU_MB1")) e->mb1 = std::max(1, atoi(v));
   if (const char* v = getenv("DCU_MB2")) e->mb2 = std::max(1, atoi(v));
   if (const char* v = getenv("DCU_RP")) e->rp = std::max(1, atoi(v));
