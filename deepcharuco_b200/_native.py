@@ -19,7 +19,7 @@ CONV_DEFAULT = CONV_TCGEN05   # tcgen05 3xTF32 tensor-core path; CONV_FFMA is th
 EXPORTS = [
     "dcu_create", "dcu_destroy", "dcu_detector_forward", "dcu_detector_forward_f32", "dcu_extract_patches",
     "dcu_decode_gather", "dcu_refine_forward", "dcu_infer_batch", "dcu_infer_batch_host",
-    "dcu_debug_conv_layer", "dcu_set_conv_impl", "dcu_launch_count", "dcu_profile_enable", "dcu_profile_read", "dcu_detector_flops_per_frame",
+    "dcu_debug_conv_layer", "dcu_debug_tc_stats", "dcu_set_conv_impl", "dcu_launch_count", "dcu_profile_enable", "dcu_profile_read", "dcu_detector_flops_per_frame",
     "dcu_refine_flops_per_patch", "dcu_last_error", "dcu_version",
 ]
 
@@ -68,6 +68,7 @@ def lib():
     L.dcu_infer_batch.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.dcu_infer_batch_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.dcu_debug_conv_layer.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]
+    L.dcu_debug_tc_stats.argtypes = [vp, i32, vp]
     L.dcu_set_conv_impl.argtypes = [vp, i32]
     L.dcu_profile_enable.argtypes = [vp, i32]
     L.dcu_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]

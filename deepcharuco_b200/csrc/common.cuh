@@ -29,6 +29,7 @@ struct ConvParams {
   float head_b;           // convPb bias
   unsigned long long* head_key;  // [n] packed (orderable heat value << 32 | ~index)
   float* heat;            // optional [n][hout][wout] dump of the heat map (tests), may be null
+  unsigned long long* stats;   // optional [8] cycle counters for the tcgen05 kernel's roles (profiling), may be null
 };
 
 // FFMA path: weights packed [cin/4][9 taps][4 cin][cout_total] with the cout axis permuted per 64-block
@@ -93,6 +94,7 @@ struct TcLayerPack {
   int cin, cout;          // cout here = N handled per CTA pass (64 or 128)
 };
 int tc_supported_shape(int cin, int cout);
+void tc_tile_arrangement(int nt, int hout, int wout, int* tr, int* tc);
 cudaError_t launch_conv3x3_tc(const ConvParams& p, const float* w_blocks, int n_slices, const void* tmap_in,
                               int sm_count, cudaStream_t s);
 

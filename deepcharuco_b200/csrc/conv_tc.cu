@@ -7,10 +7,15 @@
 //
 // Numerics.  The reference is fp32 and its outputs are quantised by arg-maxes whose top-1/top-2 margins go
 // down to ~1e-6, so single-pass TF32/BF16 is not acceptable.  Each product is formed from a
-// round-to-nearest hi/lo TF32 split of BOTH operands, a = a_hi + a_lo (22 mantissa bits), and three MMAs per
-// k-step:  a_lo*w_hi + a_hi*w_lo + a_hi*w_hi, accumulated in fp32 in TMEM ("3xTF32").  The dropped a_lo*w_lo term
-// is <= 2^-22 relative.  Weights are split offline (engine.cu: pack_tc); activations are split in shared
-// memory by a dedicated warpgroup, once per halo tile (not once per tap).
+// round-to-nearest hi/lo TF32 split of BOTH operands, a = a_hi + a_lo (22 mantissa bits), and the three products
+// a_hi*w_hi + a_hi*w_lo + a_lo*w_hi ("3xTF32"; the dropped a_lo*w_lo term is <= 2^-22 relative).  They are issued
+// as TWO MMAs per k-step:  a_hi x [w_hi | w_lo]  (N' = 2*NT, the hi and lo weight rows are adjacent in the block)
+// and  a_lo x w_hi  (N = NT, into the right half).  So each m-tile owns 2*NT TMEM columns: the left half accumulates
+// the main term, the right half the two small terms; the epilogue adds them in fp32.  This (a) cuts shared-memory
+// operand reads per k-step from 3*(A+B) to 2*A + 3*B/... (the kernel is smem-bandwidth bound at fp32 operand width) and
+// (b) keeps the small terms out of the main accumulator, whose hardware accumulation truncates once per MMA.
+// Weights are split offline (engine.cu: pack_tc); activations are split in shared memory by a dedicated warpgroup,
+// once per halo tile (not once per tap).
 //
 // Data movement.  Activations live in HBM as [n][C/4][H][W][4] fp32.  One TMA box {4, haloW, haloH, 4 groups}
 // brings a (16*TR+2) x (8*TC+2) pixel halo of 16 input channels into shared memory as planes of 16-byte
@@ -20,11 +25,14 @@
 // the same halo tile: no im2col copy, each input element is fetched from L2 once per tile (+halo).
 // Zero padding comes from TMA out-of-bounds fill.  Weight blocks (pre-packed, hi|lo) arrive by 1-D bulk copy.
 //
-// Roles (384 threads, one persistent CTA per SM, TMEM 512 columns = 2 accumulator buffers):
+// Roles (512 threads, one persistent CTA per SM).  TMEM: 512 columns = NBUF sets x MT=2 m-tiles x (main | small) x NT
+// columns; NT=64 double-buffers the set (epilogue of tile i overlaps the MMAs of tile i+1), NT=128 has one set that is
+// handed back to the MMA issuer per m-tile as the epilogue drains it:
 //   warp 0      TMA producer for activation halo chunks          (a_empty -> a_full)
 //   warp 1      tcgen05.mma issuer: warp-uniform loop, one elected lane issues (a_ready, b_full -> commits)
 //   warp 2      TMEM alloc/dealloc + bulk-copy producer for weight blocks (b_empty -> b_full)
-//   warps 4-7   epilogue: tcgen05.ld -> bias/BN/ReLU -> pool | upsample | head -> global   (acc_full -> acc_empty)
+//   warps 4-7, 12-15  epilogue, two groups (even / odd m-tiles): tcgen05.ld -> main+small -> bias/BN/ReLU ->
+//               pool | upsample | head -> global   (acc_full -> acc_empty[mt])
 //   warps 8-11  hi/lo splitter: raw fp32 halo -> tf32 hi (in place) + tf32 lo  (a_full -> a_ready)
 #include <cuda.h>
 
@@ -34,14 +42,17 @@ namespace dcu {
 
 namespace {
 
-constexpr int TC_THREADS = 384;
-constexpr int B_STAGES = 4;
+constexpr int TC_THREADS = 512;
 
 template <int NT>
 struct TcCfg {
+  // Measured on B200 (profiles/r1_tc_variants.txt): for NT=64, MT=4 single-set beats MT=2 double-buffered (7260 vs 7063
+  // frames/s): both are shared-memory-bandwidth bound and MT=4 halves the weight-block fills per MMA.
   static constexpr int MT = (NT == 64) ? 4 : 2;                 // 128-pixel m-tiles per CTA tile
+  static constexpr int NBUF = 512 / (MT * 2 * NT);              // accumulator sets in TMEM (NBUF * MT * 2*NT = 512 columns)
   static constexpr int A_STAGES = (NT == 64) ? 2 : 3;
-  static constexpr int MAX_HALO_PX = (NT == 64) ? 18 * 34 : 34 * 10;
+  static constexpr int B_STAGES = (NT == 64) ? 6 : 5;
+  static constexpr int MAX_HALO_PX = (MT == 4) ? 18 * 34 : 34 * 10;
   static constexpr int A_HALF_BYTES = 4 * MAX_HALO_PX * 16;     // 4 channel-group planes (16 channels)
   static constexpr int A_STAGE_BYTES = 2 * A_HALF_BYTES;        // hi | lo
   static constexpr int B_BLOCK_BYTES = 2 * 4 * NT * 16;         // hi | lo, 4 k-groups, NT rows, 16 B
@@ -92,6 +103,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
+}
+
+// wait + accumulate the cycles spent waiting into *acc (profiling builds of the role loops)
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
+  if (!timed) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
@@ -163,6 +182,40 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// main and small 16-column slices in flight together, one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, float* a, uint32_t tb, float* b) {
+  tmem_ld16_nowait(ta, a);
+  tmem_ld16_nowait(tb, b);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// two 32-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld32x2(uint32_t ta, float* a, uint32_t tb, float* b) {
+  tmem_ld32_nowait(ta, a);
+  tmem_ld32_nowait(tb, b);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -203,6 +256,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
                   const TcGeo g) {
   using Cfg = TcCfg<NT>;
   constexpr int MT = Cfg::MT;
+  constexpr int NBUF = Cfg::NBUF;
+  constexpr int B_STAGES = Cfg::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   uint8_t* a_smem = smem;
@@ -214,9 +269,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
   uint64_t* a_empty = a_ready + Cfg::A_STAGES;     // [A_STAGES] MMAs reading the stage retired
   uint64_t* b_full = a_empty + Cfg::A_STAGES;      // [B_STAGES]
   uint64_t* b_empty = b_full + B_STAGES;           // [B_STAGES]
-  uint64_t* acc_full = b_empty + B_STAGES;         // [2]
-  uint64_t* acc_empty = acc_full + 2;              // [2] (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_full = b_empty + B_STAGES;         // [NBUF]     all MMAs of the tile retired
+  uint64_t* acc_empty = acc_full + NBUF;           // [NBUF][MT] m-tile drained by the epilogue (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NBUF * MT);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (keeps role code on the uniform datapath)
   const int lane = threadIdx.x & 31;
@@ -232,7 +287,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 128); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < NBUF; ++i) mbar_init(&acc_full[i], 1);
+    for (int i = 0; i < NBUF * MT; ++i) mbar_init(&acc_empty[i], 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -274,13 +330,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
     }
   } else if (warp == 1) {
     // ================= MMA issuer: whole warp runs the (uniform) loop, one elected lane issues =================
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | (8u << 24);
+    constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | (8u << 24);     // f32 accum, tf32 x tf32, K-major, M = 128
+    constexpr uint32_t IDESC_2N = IDESC_BASE | ((uint32_t)((2 * NT) >> 3) << 17);          // a_hi x [w_hi | w_lo]
+    constexpr uint32_t IDESC_1N = IDESC_BASE | ((uint32_t)(NT >> 3) << 17);                // a_lo x w_hi
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     // descriptor words (cute::UMMA::SmemDescriptor): lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version(1)<<14
     const uint32_t a_desc_hi = (uint32_t)g.halo_w | (1u << 14);                 // SBO = halo_w * 16 B
     const uint32_t a_desc_lo0 = ((uint32_t)halo_px << 16);                      // LBO = plane = halo_px * 16 B
     constexpr uint32_t b_desc_hi = 8u | (1u << 14);                             // SBO = 128 B
-    constexpr uint32_t b_desc_lo0 = ((uint32_t)NT << 16);                       // LBO = NT * 16 B
+    constexpr uint32_t b_desc_lo0 = ((uint32_t)(2 * NT) << 16);                 // LBO = 2*NT * 16 B (hi rows | lo rows)
     const uint32_t a_base0 = smem_u32(a_smem) >> 4, b_base0 = smem_u32(b_smem) >> 4;   // 16-byte units from here on
     const uint32_t ks_off = 2u * (uint32_t)halo_px;                             // two channel-group planes per k-step
     uint32_t mt_off[MT];
@@ -290,55 +348,69 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
       mt_off[mt] = (uint32_t)(tri * 16 * g.halo_w + tci * 8);
     }
     int sa = 0, sb = 0, buf = 0; uint32_t pha = 0, phb = 0, phc = 0;
+    const bool timed = p.stats != nullptr;
+    long long w_a = 0, w_b = 0, w_c = 0;
+    const long long t_start = clock64();
     for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
-      mbar_wait(&acc_empty[buf], phc ^ 1u);
-      tc_fence_after();
-      const uint32_t d0 = tmem_u + (uint32_t)(buf * (MT * NT));
       for (int q = 0; q < chunks; ++q) {
-        mbar_wait(&a_ready[sa], pha);
+        mbar_wait_t(&a_ready[sa], pha, timed, w_a);
         tc_fence_after();
         const uint32_t a_hi = a_desc_lo0 + a_base0 + (uint32_t)sa * (Cfg::A_STAGE_BYTES >> 4);
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(&b_full[sb], phb);
+          mbar_wait_t(&b_full[sb], phb, timed, w_b);
           tc_fence_after();
           const int ky = tap / 3, kx = tap - 3 * ky;
           const uint32_t a_tap = a_hi + (uint32_t)(ky * g.halo_w + kx);
-          const uint32_t b_hi = b_desc_lo0 + b_base0 + (uint32_t)sb * (Cfg::B_BLOCK_BYTES >> 4);
-          if (elect_one()) {
+          const uint32_t b_blk = b_desc_lo0 + b_base0 + (uint32_t)sb * (Cfg::B_BLOCK_BYTES >> 4);
+          const bool first = (q | tap) == 0;
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
+          for (int mt = 0; mt < MT; ++mt) {
+            if (first) {                       // first touch of this m-tile's columns in this tile: wait for the epilogue
+              mbar_wait_t(&acc_empty[buf * MT + mt], phc ^ 1u, timed, w_c);
+              tc_fence_after();
+            }
+            if (elect_one()) {
+              const uint32_t d = tmem_u + (uint32_t)((buf * MT + mt) * 2 * NT);
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
                 const uint32_t da_hi = a_tap + mt_off[mt] + ks * ks_off;
                 const uint32_t da_lo = da_hi + (uint32_t)(Cfg::A_HALF_BYTES >> 4);
-                const uint32_t db_hi = b_hi + ks * (2u * NT);
-                const uint32_t db_lo = db_hi + 4u * NT;
-                const uint32_t d = d0 + (uint32_t)(mt * NT);
-                umma_tf32_w(d, da_lo, a_desc_hi, db_hi, b_desc_hi, IDESC, (q | tap | ks) ? 1u : 0u);   // small terms first
-                umma_tf32_w(d, da_hi, a_desc_hi, db_lo, b_desc_hi, IDESC, 1u);
-                umma_tf32_w(d, da_hi, a_desc_hi, db_hi, b_desc_hi, IDESC, 1u);
+                const uint32_t db = b_blk + ks * (2u * 2u * NT);              // 2 k-groups x 2*NT rows (16-byte units)
+                umma_tf32_w(d, da_hi, a_desc_hi, db, b_desc_hi, IDESC_2N, (first && ks == 0) ? 0u : 1u);   // main | a_hi*w_lo
+                umma_tf32_w(d + NT, da_lo, a_desc_hi, db, b_desc_hi, IDESC_1N, 1u);                          // + a_lo*w_hi
+              }
+              if (mt == MT - 1) {
+                umma_commit(&b_empty[sb]);
+                if (tap == 8) umma_commit(&a_empty[sa]);
+                if (tap == 8 && q == chunks - 1) umma_commit(&acc_full[buf]);
               }
             }
-            umma_commit(&b_empty[sb]);
-            if (tap == 8) umma_commit(&a_empty[sa]);
-            if (tap == 8 && q == chunks - 1) umma_commit(&acc_full[buf]);
+            __syncwarp();
           }
-          __syncwarp();
           if (++sb == B_STAGES) { sb = 0; phb ^= 1u; }
         }
         if (++sa == Cfg::A_STAGES) { sa = 0; pha ^= 1u; }
       }
-      if (++buf == 2) { buf = 0; phc ^= 1u; }
+      if (++buf == NBUF) { buf = 0; phc ^= 1u; }
     }
-  } else if (warp >= 8) {
+    if (timed && lane == 0) {
+      atomicAdd(p.stats + 0, (unsigned long long)(clock64() - t_start));   // MMA warp: total loop cycles
+      atomicAdd(p.stats + 1, (unsigned long long)w_a);                     //   waiting for split halo chunks
+      atomicAdd(p.stats + 2, (unsigned long long)w_b);                     //   waiting for weight blocks
+      atomicAdd(p.stats + 3, (unsigned long long)w_c);                     //   waiting for the epilogue to drain TMEM
+    }
+  } else if (warp >= 8 && warp < 12) {
     // ================= hi/lo splitter (128 threads) =================
     const int tid = threadIdx.x - 256;
     const int n4 = halo_px * 4;            // float4 elements in one half (4 planes)
     int st = 0; uint32_t ph = 0;
+    const bool timed = p.stats != nullptr;
+    long long w_f = 0;
+    const long long t_start = clock64();
     for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       for (int q = 0; q < chunks; ++q) {
-        mbar_wait(&a_full[st], ph);
+        mbar_wait_t(&a_full[st], ph, timed, w_f);
         float4* raw = reinterpret_cast<float4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES + Cfg::A_HALF_BYTES);
         // 4 independent 16-byte loads in flight per thread, then the 8 stores
@@ -366,32 +438,48 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
         if (++st == Cfg::A_STAGES) { st = 0; ph ^= 1u; }
       }
     }
+    if (timed && tid == 0) {
+      atomicAdd(p.stats + 4, (unsigned long long)(clock64() - t_start));   // splitter: total loop cycles
+      atomicAdd(p.stats + 5, (unsigned long long)w_f);                     //   waiting for TMA halo chunks
+    }
   } else if (warp >= 4) {
-    // ================= epilogue (128 threads; warp w reads TMEM lanes 32*(w%4) ..) =================
+    // ================= epilogue (2 groups x 128 threads; warp w reads TMEM lanes 32*(w%4) ..) =================
+    constexpr int CW = 16;                 // accumulator columns (channels) per step
+    const int grp = (warp >= 12) ? 1 : 0;  // group 0 drains even m-tiles, group 1 odd ones
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;          // accumulator row = pixel index inside the 16x8 m-tile
     const int prow = m >> 3, pcol = m & 7;
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
     const int cg_out = p.cout_total >> 2;
-    int buf = 0; uint32_t phc = 0;
+    uint32_t phc = 0;
+    int buf = 0;
+    const bool timed = p.stats != nullptr;
+    long long w_e = 0;
+    const long long t_start = clock64();
     for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       const TileCoord c = decode_tile(t, g);
-      mbar_wait(&acc_full[buf], phc);
+      mbar_wait_t(&acc_full[buf], phc, timed, w_e);
       tc_fence_after();
       const int ch_base = c.slice * NT;
 #pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
+      for (int mt = grp; mt < MT; mt += 2) {
         const int tri = mt / g.tc, tci = mt - tri * g.tc;
         const int oy = c.y0 + tri * 16 + prow, ox = c.x0 + tci * 8 + pcol;
         const bool inb = (oy < p.hout) && (ox < p.wout);
         float head_sum = 0.f;
 #pragma unroll 1
-        for (int cc = 0; cc < NT / 32; ++cc) {
-          float v[32];
-          tmem_ld32(tmem_base + lane_addr + (uint32_t)(buf * (MT * NT) + mt * NT + cc * 32), v);
-          const int ch0 = ch_base + cc * 32;
+        for (int cc = 0; cc < NT / CW; ++cc) {
+          float v[CW];
+          {
+            float sm[CW];
+            const uint32_t col = (uint32_t)((buf * MT + mt) * 2 * NT + cc * CW);
+            tmem_ld16x2(tmem_base + lane_addr + col, v, tmem_base + lane_addr + col + NT, sm);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < CW; ++j) v[j] += sm[j];        // main term + (a_hi*w_lo + a_lo*w_hi)
+          }
+          const int ch0 = ch_base + cc * CW;
+#pragma unroll
+          for (int j = 0; j < CW; j += 4) {
             const float4 bi = *reinterpret_cast<const float4*>(&prm[ch0 + j]);
             const float4 al = *reinterpret_cast<const float4*>(&prm[512 + ch0 + j]);
             const float4 be = *reinterpret_cast<const float4*>(&prm[1024 + ch0 + j]);
@@ -402,10 +490,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
           }
           if (p.head_w != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) head_sum = fmaf(v[j], __ldg(p.head_w + cc * 32 + j), head_sum);
+            for (int j = 0; j < CW; ++j) head_sum = fmaf(v[j], __ldg(p.head_w + cc * CW + j), head_sum);
           } else if (p.pool) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < CW; ++j) {
               float x = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));   // column partner
               v[j] = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));            // row partner
             }
@@ -413,14 +501,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
             if (((lane & 9) == 0) && (oy >> 1) < hp && (ox >> 1) < wp) {
               float4* o = reinterpret_cast<float4*>(p.out) + (((size_t)c.img * cg_out + (ch0 >> 2)) * hp + (oy >> 1)) * wp + (ox >> 1);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) o[(size_t)k * hp * wp] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+              for (int k = 0; k < CW / 4; ++k) o[(size_t)k * hp * wp] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
             }
           } else if (p.ups) {
             if (inb) {
               const int hu = p.hout * 2, wu = p.wout * 2;
               float4* o = reinterpret_cast<float4*>(p.out) + (((size_t)c.img * cg_out + (ch0 >> 2)) * hu + 2 * oy) * wu + 2 * ox;
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
+              for (int k = 0; k < CW / 4; ++k) {
                 const float4 x = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                 float4* ok = o + (size_t)k * hu * wu;
                 ok[0] = x; ok[1] = x; ok[wu] = x; ok[wu + 1] = x;
@@ -430,7 +518,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
             if (inb) {
               float4* o = reinterpret_cast<float4*>(p.out) + (((size_t)c.img * cg_out + (ch0 >> 2)) * p.hout + oy) * p.wout + ox;
 #pragma unroll
-              for (int k = 0; k < 8; ++k) o[(size_t)k * p.hout * p.wout] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+              for (int k = 0; k < CW / 4; ++k) o[(size_t)k * p.hout * p.wout] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
             }
           }
         }
@@ -450,10 +538,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
           }
           if (lane == 0 && key != 0ull) atomicMax(p.head_key + c.img, key);
         }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf * MT + mt]);   // these columns may now be overwritten by a later tile's MMAs
       }
-      tc_fence_before();
-      mbar_arrive(&acc_empty[buf]);
-      if (++buf == 2) { buf = 0; phc ^= 1u; }
+      if (++buf == NBUF) { buf = 0; phc ^= 1u; }
+    }
+    if (timed && (threadIdx.x == 128 || threadIdx.x == 384)) {
+      atomicAdd(p.stats + 6, (unsigned long long)(clock64() - t_start) / 2);   // epilogue: total loop cycles (avg of 2 groups)
+      atomicAdd(p.stats + 7, (unsigned long long)w_e / 2);                     //   waiting for MMAs
     }
   }
 
@@ -467,6 +559,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
 }
 
 }  // namespace
+
+// m-tile arrangement (TR x TC tiles of 16 rows x 8 cols) per CTA tile; also sizes the TMA box (engine.cu)
+void tc_tile_arrangement(int nt, int hout, int wout, int* tr, int* tc) {
+  if (nt == 64) {               // MT = 4
+    if (wout >= 32) { *tr = 1; *tc = 4; }
+    else if (hout > 16 && wout > 8) { *tr = 2; *tc = 2; }
+    else { *tr = 1; *tc = 4; }
+    return;
+  }
+  // MT = 2
+  if (wout % 16 == 0 || wout > 40) { *tr = 1; *tc = 2; }
+  else if (hout > 16) { *tr = 2; *tc = 1; }
+  else { *tr = 1; *tc = 2; }
+}
 
 int tc_supported_shape(int cin, int cout) {
   if (cin % 16 != 0 || cin > 128) return 0;
@@ -486,16 +592,8 @@ static cudaError_t launch_nt(const ConvParams& p, const float* w_blocks, int n_s
     attr_done = true;
   }
   TcGeo g;
-  // arrangement must match engine.cu:tc_geom (the TMA box is built from it)
-  if (NT == 64) {
-    if (p.wout >= 32) { g.tr = 1; g.tc = 4; }
-    else if (p.hout > 16 && p.wout > 8) { g.tr = 2; g.tc = 2; }
-    else { g.tr = 1; g.tc = 4; }
-  } else {
-    if (p.wout % 16 == 0 || p.wout > 40) { g.tr = 1; g.tc = 2; }
-    else if (p.hout > 16) { g.tr = 2; g.tc = 1; }
-    else { g.tr = 1; g.tc = 2; }
-  }
+  tc_tile_arrangement(NT, p.hout, p.wout, &g.tr, &g.tc);
+  if (g.tr * g.tc != Cfg::MT) return cudaErrorInvalidValue;
   g.halo_w = 8 * g.tc + 2; g.halo_h = 16 * g.tr + 2;
   if (g.halo_w * g.halo_h > Cfg::MAX_HALO_PX) return cudaErrorInvalidValue;
   g.tiles_x = ceil_div(p.wout, 8 * g.tc); g.tiles_y = ceil_div(p.hout, 16 * g.tr);

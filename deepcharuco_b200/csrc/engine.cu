@@ -94,7 +94,8 @@ inline float tf32_rn(float x) {
 }
 
 // tcgen05 weight blocks: for slice s (NT output channels), chunk q (16 input channels), tap t:
-//   block[(s*chunks + q)*9 + t] = { hi[4 kgroups][NT][4], lo[4 kgroups][NT][4] }   (floats)
+//   block[(s*chunks + q)*9 + t] = [4 kgroups][2*NT rows: NT hi rows then NT lo rows][4]   (floats)
+// so that [w_hi | w_lo] is ONE K-major operand with N' = 2*NT (conv_tc.cu issues a_hi x [w_hi|w_lo] as a single MMA).
 std::vector<float> pack_tc(const std::vector<const float*>& ws, const std::vector<int>& couts, int cin, int nt) {
   int cout_total = 0;
   for (int c : couts) cout_total += c;
@@ -118,8 +119,8 @@ std::vector<float> pack_tc(const std::vector<const float*>& ws, const std::vecto
               const float w = row[s * nt + n][(size_t)ci * 9 + tap];
               const float hi = tf32_rn(w);
               const float lo = tf32_rn(w - hi);
-              b[((size_t)kg * nt + n) * 4 + e] = hi;
-              b[(size_t)4 * nt * 4 + ((size_t)kg * nt + n) * 4 + e] = lo;
+              b[((size_t)kg * 2 * nt + n) * 4 + e] = hi;
+              b[((size_t)kg * 2 * nt + nt + n) * 4 + e] = lo;
             }
       }
   return out;
@@ -143,18 +144,11 @@ PFN_encodeTiled get_encode() {
 
 }  // namespace
 
-// tile arrangement chosen for the tcgen05 kernel (conv_tc.cu): MT m-tiles of 16x8 pixels as TR x TC
 struct TcGeom { int tr, tc; };
 static TcGeom tc_geom(int nt, int hout, int wout) {
-  if (nt == 64) {               // MT = 4
-    if (wout >= 32) return {1, 4};
-    if (hout > 16 && wout > 8) return {2, 2};
-    return {1, 4};
-  }
-  // MT = 2
-  if (wout % 16 == 0 || wout > 40) return {1, 2};
-  if (hout > 16) return {2, 1};
-  return {1, 2};
+  TcGeom g;
+  tc_tile_arrangement(nt, hout, wout, &g.tr, &g.tc);   // single source of truth: conv_tc.cu
+  return g;
 }
 
 struct DcuEngine {
@@ -281,6 +275,7 @@ static int make_tmap(CUtensorMap* tm, const float* base, int n, int cin, int h, 
 }
 
 struct HeadFuse { const float* w = nullptr; float b = 0.f; unsigned long long* keys = nullptr; float* heat = nullptr; };
+static unsigned long long* g_tc_stats = nullptr;   // device [8]; set by dcu_debug_tc_stats (profiling only)
 
 static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, float* out, int n, int hin, int win,
                    const HeadFuse* hf, cudaStream_t s) {
@@ -289,6 +284,7 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
   p.n = n; p.cin = l.cin; p.cout_total = l.cout; p.hin = hin; p.win = win;
   p.hout = hin + 2 * l.pad - 2; p.wout = win + 2 * l.pad - 2; p.pad = l.pad; p.pool = l.pool; p.ups = l.ups;
   if (hf) { p.head_w = hf->w; p.head_b = hf->b; p.head_key = hf->keys; p.heat = hf->heat; }
+  p.stats = g_tc_stats;
   if (n <= 0) return DCU_OK;
   e->prof_begin(0, 2.0 * 9.0 * l.cin * l.cout * (double)p.hout * p.wout * n, s);
   if (impl == DCU_CONV_TCGEN05) {
@@ -723,6 +719,21 @@ int dcu_infer_batch_host(DcuEngine* e, const uint8_t* frames_host, int n, int du
   if (total > e->cfg.max_patches)
     return fail(DCU_ERR_CAPACITY, "corner count " + std::to_string(total) + " exceeds max_patches " +
                                       std::to_string(e->cfg.max_patches));
+  return DCU_OK;
+}
+
+int dcu_debug_tc_stats(DcuEngine* e, int enable, uint64_t* out8) {
+  if (!e) return fail(DCU_ERR_INVALID, "null engine");
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaDeviceSynchronize());
+  if (out8 && g_tc_stats) CK(cudaMemcpy(out8, g_tc_stats, 64, cudaMemcpyDeviceToHost));
+  if (enable) {
+    if (!g_tc_stats) CK(cudaMalloc(&g_tc_stats, 64));
+    CK(cudaMemset(g_tc_stats, 0, 64));
+  } else if (g_tc_stats) {
+    cudaFree(g_tc_stats);
+    g_tc_stats = nullptr;
+  }
   return DCU_OK;
 }
 

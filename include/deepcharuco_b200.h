@@ -142,6 +142,11 @@ int dcu_infer_batch_host(DcuEngine* e, const uint8_t* frames_host, int n, int du
 int dcu_debug_conv_layer(DcuEngine* e, int net, int layer, int conv_impl, const float* in_dev,
                          int n, int h, int w, float* out_dev, void* stream);
 
+/* Profiling hook for the tcgen05 kernel: enable != 0 zeroes and arms eight device cycle counters that the kernel's
+ * roles add to (MMA warp: total / wait halo / wait weights / wait epilogue; splitter: total / wait TMA; epilogue:
+ * total / wait MMA), summed over CTAs; out8 (may be NULL) receives the counters accumulated so far. */
+int dcu_debug_tc_stats(DcuEngine* e, int enable, uint64_t* out8);
+
 /* Select the 3x3 conv implementation after creation (DCU_CONV_*). */
 int dcu_set_conv_impl(DcuEngine* e, int conv_impl);
 
