@@ -29,6 +29,7 @@ struct ConvParams {
   float head_b;           // convPb bias
   unsigned long long* head_key;  // [n] packed (orderable heat value << 32 | ~index)
   float* heat;            // optional [n][hout][wout] dump of the heat map (tests), may be null
+  float wscale_inv;       // tcgen05 path: 2^-s, undoes the power-of-two weight scaling of the fp16 split (1.0 otherwise)
   unsigned long long* stats;   // optional [8] cycle counters for the tcgen05 kernel's roles (profiling), may be null
 };
 
@@ -90,7 +91,7 @@ void launch_c4_to_nchw(const float* in, float* out, int n, int c, int h, int w, 
 
 // tcgen05 path (conv_tc.cu)
 struct TcLayerPack {
-  const float* w_blocks;  // per (chunk of 16 cin, tap): [hi|lo][4 k-groups][N][4] floats
+  const float* w_blocks;  // per (chunk of 16 cin, tap): [2 k-groups][N hi rows | N lo rows][8] fp16
   int cin, cout;          // cout here = N handled per CTA pass (64 or 128)
 };
 int tc_supported_shape(int cin, int cout);

@@ -6,22 +6,27 @@
 // arg-max), /root/reference/src/models/net.py:60-77 and refinenet.py:56-81.
 //
 // Numerics.  The reference is fp32 and its outputs are quantised by arg-maxes whose top-1/top-2 margins go
-// down to ~1e-6, so single-pass TF32/BF16 is not acceptable.  Each product is formed from a
-// round-to-nearest hi/lo TF32 split of BOTH operands, a = a_hi + a_lo (22 mantissa bits), and the three products
-// a_hi*w_hi + a_hi*w_lo + a_lo*w_hi ("3xTF32"; the dropped a_lo*w_lo term is <= 2^-22 relative).  They are issued
-// as TWO MMAs per k-step:  a_hi x [w_hi | w_lo]  (N' = 2*NT, the hi and lo weight rows are adjacent in the block)
-// and  a_lo x w_hi  (N = NT, into the right half).  So each m-tile owns 2*NT TMEM columns: the left half accumulates
-// the main term, the right half the two small terms; the epilogue adds them in fp32.  This (a) cuts shared-memory
-// operand reads per k-step from 3*(A+B) to 2*A + 3*B/... (the kernel is smem-bandwidth bound at fp32 operand width) and
-// (b) keeps the small terms out of the main accumulator, whose hardware accumulation truncates once per MMA.
-// Weights are split offline (engine.cu: pack_tc); activations are split in shared memory by a dedicated warpgroup,
-// once per halo tile (not once per tap).
+// down to ~1e-6, so a single low-precision pass is not acceptable.  Each operand is split into
+// two fp16 numbers, x = x_hi + x_lo with x_hi = fp16(x), x_lo = fp16(x - x_hi): 2 x 11 significant bits, the same
+// 22 bits a TF32 hi/lo split keeps, but at half the bytes per element and twice the tensor-pipe rate.  Weights
+// are pre-multiplied by a per-layer power of two (exact) so that w_lo stays in fp16's normal range; the epilogue
+// multiplies the accumulator back by 2^-s (exact).  Activations are post-ReLU values of magnitude <= ~1e2; an
+// activation below 2^-14*2^11 only loses bits whose weight is below one fp32 ulp of the accumulator (checked
+// against the fp32 oracle: same logit / heat-map error as the TF32 split, tools/emulate_split.py).
+// The three products a_hi*w_hi + a_hi*w_lo + a_lo*w_hi (a_lo*w_lo <= 2^-22 relative is dropped) are issued as
+// TWO kind::f16 MMAs per (tap, 16-channel chunk):  a_hi x [w_hi | w_lo]  (N' = 2*NT, hi and lo weight rows are
+// adjacent in the block) and  a_lo x w_hi  (N = NT, into the right half).  Each m-tile therefore owns 2*NT TMEM
+// columns: the left half accumulates the main term, the right half the two small terms; the epilogue adds them
+// in fp32.  This keeps the small terms out of the main accumulator (the hardware accumulation truncates once per
+// MMA) and reads a_hi from shared memory once for both weight halves -- the kernel is shared-memory-bandwidth bound.
+// Weights are split offline (engine.cu: pack_tc); activations are converted in shared memory by a dedicated
+// warpgroup, once per halo tile (not once per tap).
 //
 // Data movement.  Activations live in HBM as [n][C/4][H][W][4] fp32.  One TMA box {4, haloW, haloH, 4 groups}
 // brings a (16*TR+2) x (8*TC+2) pixel halo of 16 input channels into shared memory as planes of 16-byte
-// pixels.  In that layout any run of 8 horizontally adjacent pixels IS a no-swizzle K-major core matrix
-// (8 rows x 16 B), consecutive image rows are SBO = haloW*16 B apart and the next 4 channels are LBO = plane
-// bytes apart -- so all nine taps of the convolution are just nine different descriptor start addresses into
+// pixels (4 fp32 channels); the converter rewrites them as fp16 planes of 16-byte pixels (8 channels).  In that
+// layout any run of 8 horizontally adjacent pixels IS a no-swizzle K-major core matrix (8 rows x 16 B),
+// consecutive image rows are SBO = haloW*16 B apart and the next 8 channels are LBO = plane bytes apart -- so all nine taps of the convolution are just nine different descriptor start addresses into
 // the same halo tile: no im2col copy, each input element is fetched from L2 once per tile (+halo).
 // Zero padding comes from TMA out-of-bounds fill.  Weight blocks (pre-packed, hi|lo) arrive by 1-D bulk copy.
 //
@@ -33,8 +38,9 @@
 //   warp 2      TMEM alloc/dealloc + bulk-copy producer for weight blocks (b_empty -> b_full)
 //   warps 4-7, 12-15  epilogue, two groups (even / odd m-tiles): tcgen05.ld -> main+small -> bias/BN/ReLU ->
 //               pool | upsample | head -> global   (acc_full -> acc_empty[mt])
-//   warps 8-11  hi/lo splitter: raw fp32 halo -> tf32 hi (in place) + tf32 lo  (a_full -> a_ready)
+//   warps 8-11  hi/lo converter: raw fp32 halo planes -> fp16 hi planes + fp16 lo planes  (a_full -> a_ready)
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -51,11 +57,12 @@ struct TcCfg {
   static constexpr int MT = (NT == 64) ? 4 : 2;                 // 128-pixel m-tiles per CTA tile
   static constexpr int NBUF = 512 / (MT * 2 * NT);              // accumulator sets in TMEM (NBUF * MT * 2*NT = 512 columns)
   static constexpr int A_STAGES = (NT == 64) ? 2 : 3;
-  static constexpr int B_STAGES = (NT == 64) ? 6 : 5;
+  static constexpr int B_STAGES = 8;
   static constexpr int MAX_HALO_PX = (MT == 4) ? 18 * 34 : 34 * 10;
-  static constexpr int A_HALF_BYTES = 4 * MAX_HALO_PX * 16;     // 4 channel-group planes (16 channels)
-  static constexpr int A_STAGE_BYTES = 2 * A_HALF_BYTES;        // hi | lo
-  static constexpr int B_BLOCK_BYTES = 2 * 4 * NT * 16;         // hi | lo, 4 k-groups, NT rows, 16 B
+  static constexpr int A_RAW_BYTES = 4 * MAX_HALO_PX * 16;      // TMA landing zone: 4 planes of 4 fp32 channels
+  static constexpr int A_HALF_BYTES = 2 * MAX_HALO_PX * 16;     // fp16 hi (or lo): 2 planes of 8 channels
+  static constexpr int A_STAGE_BYTES = A_RAW_BYTES + 2 * A_HALF_BYTES;   // raw | hi | lo
+  static constexpr int B_BLOCK_BYTES = 2 * (2 * NT) * 16;       // 2 k-groups x (NT hi rows + NT lo rows) x 8 fp16
   static constexpr int PARAM_BYTES = 3 * 512 * 4;               // bias / alpha / beta for up to 512 channels
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_BLOCK_BYTES + PARAM_BYTES + BAR_BYTES + 128;
@@ -130,17 +137,8 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
 // 64-bit descriptors passed as two 32-bit halves: only the low word (start address field) changes between MMAs
-__device__ __forceinline__ void umma_tf32_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+__device__ __forceinline__ void umma_f16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                             uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n"
@@ -149,7 +147,7 @@ __device__ __forceinline__ void umma_tf32_w(uint32_t d_tmem, uint32_t a_lo, uint
       "mov.b64 da, {%1, %2};\n"
       "mov.b64 db, {%3, %4};\n"
       "setp.ne.b32 p, %6, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
       "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
       : "memory");
 }
@@ -224,10 +222,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
   return d;
-}
-
-__device__ __forceinline__ float tf32_rn(float x) {
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 __device__ __forceinline__ unsigned int orderable(float v) {
@@ -330,7 +324,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
     }
   } else if (warp == 1) {
     // ================= MMA issuer: whole warp runs the (uniform) loop, one elected lane issues =================
-    constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | (8u << 24);     // f32 accum, tf32 x tf32, K-major, M = 128
+    constexpr uint32_t IDESC_BASE = (1u << 4) | (0u << 7) | (0u << 10) | (8u << 24);     // f32 accum, f16 x f16, K-major, M = 128, K = 16
     constexpr uint32_t IDESC_2N = IDESC_BASE | ((uint32_t)((2 * NT) >> 3) << 17);          // a_hi x [w_hi | w_lo]
     constexpr uint32_t IDESC_1N = IDESC_BASE | ((uint32_t)(NT >> 3) << 17);                // a_lo x w_hi
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -340,7 +334,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
     constexpr uint32_t b_desc_hi = 8u | (1u << 14);                             // SBO = 128 B
     constexpr uint32_t b_desc_lo0 = ((uint32_t)(2 * NT) << 16);                 // LBO = 2*NT * 16 B (hi rows | lo rows)
     const uint32_t a_base0 = smem_u32(a_smem) >> 4, b_base0 = smem_u32(b_smem) >> 4;   // 16-byte units from here on
-    const uint32_t ks_off = 2u * (uint32_t)halo_px;                             // two channel-group planes per k-step
     uint32_t mt_off[MT];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
@@ -355,7 +348,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
       for (int q = 0; q < chunks; ++q) {
         mbar_wait_t(&a_ready[sa], pha, timed, w_a);
         tc_fence_after();
-        const uint32_t a_hi = a_desc_lo0 + a_base0 + (uint32_t)sa * (Cfg::A_STAGE_BYTES >> 4);
+        const uint32_t a_hi = a_desc_lo0 + a_base0 + (uint32_t)sa * (Cfg::A_STAGE_BYTES >> 4) + (uint32_t)(Cfg::A_RAW_BYTES >> 4);
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait_t(&b_full[sb], phb, timed, w_b);
@@ -372,14 +365,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
             }
             if (elect_one()) {
               const uint32_t d = tmem_u + (uint32_t)((buf * MT + mt) * 2 * NT);
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint32_t da_hi = a_tap + mt_off[mt] + ks * ks_off;
-                const uint32_t da_lo = da_hi + (uint32_t)(Cfg::A_HALF_BYTES >> 4);
-                const uint32_t db = b_blk + ks * (2u * 2u * NT);              // 2 k-groups x 2*NT rows (16-byte units)
-                umma_tf32_w(d, da_hi, a_desc_hi, db, b_desc_hi, IDESC_2N, (first && ks == 0) ? 0u : 1u);   // main | a_hi*w_lo
-                umma_tf32_w(d + NT, da_lo, a_desc_hi, db, b_desc_hi, IDESC_1N, 1u);                          // + a_lo*w_hi
-              }
+              const uint32_t da_hi = a_tap + mt_off[mt];
+              const uint32_t da_lo = da_hi + (uint32_t)(Cfg::A_HALF_BYTES >> 4);
+              umma_f16_w(d, da_hi, a_desc_hi, b_blk, b_desc_hi, IDESC_2N, first ? 0u : 1u);      // main | a_hi*w_lo
+              umma_f16_w(d + NT, da_lo, a_desc_hi, b_blk, b_desc_hi, IDESC_1N, 1u);              // + a_lo*w_hi
               if (mt == MT - 1) {
                 umma_commit(&b_empty[sb]);
                 if (tap == 8) umma_commit(&a_empty[sa]);
@@ -403,7 +392,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
   } else if (warp >= 8 && warp < 12) {
     // ================= hi/lo splitter (128 threads) =================
     const int tid = threadIdx.x - 256;
-    const int n4 = halo_px * 4;            // float4 elements in one half (4 planes)
     int st = 0; uint32_t ph = 0;
     const bool timed = p.stats != nullptr;
     long long w_f = 0;
@@ -411,25 +399,39 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
     for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       for (int q = 0; q < chunks; ++q) {
         mbar_wait_t(&a_full[st], ph, timed, w_f);
-        float4* raw = reinterpret_cast<float4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES + Cfg::A_HALF_BYTES);
-        // 4 independent 16-byte loads in flight per thread, then the 8 stores
-        for (int i0 = tid; i0 < n4; i0 += 4 * 128) {
-          float4 v[4];
+        const float4* raw = reinterpret_cast<const float4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES);
+        uint4* hi = reinterpret_cast<uint4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES + Cfg::A_RAW_BYTES);
+        uint4* lo = reinterpret_cast<uint4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES + Cfg::A_RAW_BYTES + Cfg::A_HALF_BYTES);
+        // item = (k-group kg of 8 channels, pixel): two fp32 planes (4+4 channels) -> one fp16 hi pixel + one fp16 lo pixel
+        const int n_items = 2 * halo_px;
+        for (int i0 = tid; i0 < n_items; i0 += 2 * 128) {
+          float4 va[2], vb[2];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 2; ++u) {
             const int i = i0 + u * 128;
-            v[u] = (i < n4) ? raw[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n_items) {
+              const int kg = (i >= halo_px) ? 1 : 0, px = i - kg * halo_px;
+              va[u] = raw[(2 * kg) * halo_px + px];
+              vb[u] = raw[(2 * kg + 1) * halo_px + px];
+            }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 2; ++u) {
             const int i = i0 + u * 128;
-            if (i < n4) {
-              float4 h, l;
-              h.x = tf32_rn(v[u].x); h.y = tf32_rn(v[u].y); h.z = tf32_rn(v[u].z); h.w = tf32_rn(v[u].w);
-              l.x = tf32_rn(v[u].x - h.x); l.y = tf32_rn(v[u].y - h.y); l.z = tf32_rn(v[u].z - h.z); l.w = tf32_rn(v[u].w - h.w);
-              raw[i] = h;
-              lo[i] = l;
+            if (i < n_items) {
+              const float f[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float x0 = fminf(f[2 * e], 65504.f), x1 = fminf(f[2 * e + 1], 65504.f);   // post-ReLU inputs: >= 0
+                const __half2 hh = __floats2half2_rn(x0, x1);
+                const float2 hf = __half22float2(hh);
+                const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+              }
+              hi[i] = make_uint4(h[0], h[1], h[2], h[3]);
+              lo[i] = make_uint4(l[0], l[1], l[2], l[3]);
             }
           }
         }
@@ -475,7 +477,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
             const uint32_t col = (uint32_t)((buf * MT + mt) * 2 * NT + cc * CW);
             tmem_ld16x2(tmem_base + lane_addr + col, v, tmem_base + lane_addr + col + NT, sm);
 #pragma unroll
-            for (int j = 0; j < CW; ++j) v[j] += sm[j];        // main term + (a_hi*w_lo + a_lo*w_hi)
+            for (int j = 0; j < CW; ++j) v[j] = (v[j] + sm[j]) * p.wscale_inv;   // main + (a_hi*w_lo + a_lo*w_hi), undo 2^s
           }
           const int ch0 = ch_base + cc * CW;
 #pragma unroll

@@ -3,6 +3,7 @@
 // inference.infer_image (/root/reference/src/inference.py:41-60) for whole batches.
 #include <cuda_runtime.h>
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cmath>
@@ -47,6 +48,7 @@ struct Layer3x3 {
   int pad = 1, pool = 0, ups = 0;
   DevBuf w_ffma;              // [cin/4][9][4][cout]
   DevBuf w_tc;                // tcgen05 blocks (conv_tc.cu layout), empty if shape unsupported
+  float tc_scale = 1.f;       // power-of-two weight scale baked into w_tc
   int tc_nt = 0;              // N per CTA pass for the tcgen05 kernel (64 / 128), 0 = unsupported
   DevBuf bias, alpha, beta;   // [cout]
 };
@@ -85,23 +87,24 @@ cudaError_t upload(DevBuf& b, const std::vector<float>& h) {
   return cudaMemcpy(b.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
 }
 
-// hi/lo split used by the tcgen05 path: round-to-nearest to 10 explicit mantissa bits (TF32)
-inline float tf32_rn(float x) {
-  uint32_t b; std::memcpy(&b, &x, 4);
-  b = (b + 0x1000u) & 0xffffe000u;
-  float r; std::memcpy(&r, &b, 4);
-  return r;
+// tcgen05 weight blocks (fp16 hi/lo split, conv_tc.cu).  For slice s (NT output channels), chunk q (16 input
+// channels), tap t:   block[(s*chunks + q)*9 + t] = [2 k-groups of 8 channels][2*NT rows: NT hi rows then NT lo rows][8 fp16]
+// so that [w_hi | w_lo] is ONE K-major operand with N' = 2*NT.  Weights are pre-multiplied by `scale` (a power of two,
+// exact) so that w_lo = fp16(w*scale - w_hi) stays in fp16's normal range; the kernel's epilogue multiplies by 1/scale.
+float tc_weight_scale(const std::vector<const float*>& ws, const std::vector<int>& couts, int cin) {
+  float mx = 0.f;
+  for (size_t t = 0; t < ws.size(); ++t)
+    for (size_t i = 0; i < (size_t)couts[t] * cin * 9; ++i) mx = std::max(mx, std::fabs(ws[t][i]));
+  if (!(mx > 0.f)) return 1.f;
+  return std::exp2(std::floor(std::log2(32768.0f / mx)));      // |w*scale| < 65504 with a 2x margin
 }
 
-// tcgen05 weight blocks: for slice s (NT output channels), chunk q (16 input channels), tap t:
-//   block[(s*chunks + q)*9 + t] = [4 kgroups][2*NT rows: NT hi rows then NT lo rows][4]   (floats)
-// so that [w_hi | w_lo] is ONE K-major operand with N' = 2*NT (conv_tc.cu issues a_hi x [w_hi|w_lo] as a single MMA).
-std::vector<float> pack_tc(const std::vector<const float*>& ws, const std::vector<int>& couts, int cin, int nt) {
+std::vector<uint16_t> pack_tc(const std::vector<const float*>& ws, const std::vector<int>& couts, int cin, int nt, float scale) {
   int cout_total = 0;
   for (int c : couts) cout_total += c;
   const int slices = cout_total / nt, chunks = cin / 16;
-  const size_t blk = (size_t)2 * 4 * nt * 4;
-  std::vector<float> out((size_t)slices * chunks * 9 * blk);
+  const size_t blk = (size_t)2 * (2 * nt) * 8;      // halves per block
+  std::vector<uint16_t> out((size_t)slices * chunks * 9 * blk);
   std::vector<const float*> row(cout_total);
   {
     int o = 0;
@@ -111,16 +114,18 @@ std::vector<float> pack_tc(const std::vector<const float*>& ws, const std::vecto
   for (int s = 0; s < slices; ++s)
     for (int q = 0; q < chunks; ++q)
       for (int tap = 0; tap < 9; ++tap) {
-        float* b = out.data() + (((size_t)s * chunks + q) * 9 + tap) * blk;
-        for (int kg = 0; kg < 4; ++kg)
+        uint16_t* b = out.data() + (((size_t)s * chunks + q) * 9 + tap) * blk;
+        for (int kg = 0; kg < 2; ++kg)
           for (int n = 0; n < nt; ++n)
-            for (int e = 0; e < 4; ++e) {
-              const int ci = q * 16 + kg * 4 + e;
-              const float w = row[s * nt + n][(size_t)ci * 9 + tap];
-              const float hi = tf32_rn(w);
-              const float lo = tf32_rn(w - hi);
-              b[((size_t)kg * 2 * nt + n) * 4 + e] = hi;
-              b[((size_t)kg * 2 * nt + nt + n) * 4 + e] = lo;
+            for (int e = 0; e < 8; ++e) {
+              const int ci = q * 16 + kg * 8 + e;
+              const float w = row[s * nt + n][(size_t)ci * 9 + tap] * scale;
+              const __half hi = __float2half_rn(w);
+              const __half lo = __float2half_rn(w - __half2float(hi));
+              uint16_t hb, lb;
+              std::memcpy(&hb, &hi, 2); std::memcpy(&lb, &lo, 2);
+              b[((size_t)kg * 2 * nt + n) * 8 + e] = hb;
+              b[((size_t)kg * 2 * nt + nt + n) * 8 + e] = lb;
             }
       }
   return out;
@@ -251,7 +256,12 @@ int build_3x3(Layer3x3& l, std::vector<const DcuConvLayer*> parts, int pad, int 
   CK(upload(l.alpha, concat(as, couts)));
   CK(upload(l.beta, concat(es, couts)));
   l.tc_nt = tc_supported_shape(cin, l.cout);
-  if (l.tc_nt > 0) CK(upload(l.w_tc, pack_tc(ws, couts, cin, l.tc_nt)));
+  if (l.tc_nt > 0) {
+    l.tc_scale = tc_weight_scale(ws, couts, cin);
+    const std::vector<uint16_t> blocks = pack_tc(ws, couts, cin, l.tc_nt, l.tc_scale);
+    CK(l.w_tc.alloc(blocks.size() * 2));
+    CK(cudaMemcpy(l.w_tc.p, blocks.data(), blocks.size() * 2, cudaMemcpyHostToDevice));
+  }
   return DCU_OK;
 }
 
@@ -285,6 +295,7 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
   p.hout = hin + 2 * l.pad - 2; p.wout = win + 2 * l.pad - 2; p.pad = l.pad; p.pool = l.pool; p.ups = l.ups;
   if (hf) { p.head_w = hf->w; p.head_b = hf->b; p.head_key = hf->keys; p.heat = hf->heat; }
   p.stats = g_tc_stats;
+  p.wscale_inv = (impl == DCU_CONV_TCGEN05) ? 1.0f / l.tc_scale : 1.0f;
   if (n <= 0) return DCU_OK;
   e->prof_begin(0, 2.0 * 9.0 * l.cin * l.cout * (double)p.hout * p.wout * n, s);
   if (impl == DCU_CONV_TCGEN05) {

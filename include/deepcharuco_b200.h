@@ -42,7 +42,7 @@ extern "C" {
 /* Which convolution implementation the engine uses for the 3x3 layers with Cin >= 64.
  * Both are this library's own sm_100a kernels; neither is a fallback to a library. */
 #define DCU_CONV_FFMA   0      /* fp32 CUDA-core direct convolution (bring-up / strict-fp32 path) */
-#define DCU_CONV_TCGEN05 1     /* tcgen05.mma kind::tf32, 3-term hi/lo split, fp32 accumulate in TMEM */
+#define DCU_CONV_TCGEN05 1     /* tcgen05.mma kind::f16 on an fp16 hi/lo split of both operands (3 products, 22 bits), fp32 accumulate in TMEM */
 
 typedef struct DcuEngine DcuEngine;
 
