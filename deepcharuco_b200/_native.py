@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdeepcharuco_b200.so")
+LIB_PATH = os.environ.get("DCU_LIB_PATH") or os.path.join(_HERE, "libdeepcharuco_b200.so")   # env override: A/B builds
 
 DCU_OK, DCU_ERR_INVALID, DCU_ERR_CUDA, DCU_ERR_CAPACITY, DCU_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 CONV_FFMA, CONV_TCGEN05 = 0, 1

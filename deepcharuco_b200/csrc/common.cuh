@@ -96,7 +96,7 @@ struct TcLayerPack {
 };
 int tc_supported_shape(int cin, int cout);
 void tc_tile_arrangement(int nt, int hout, int wout, int* tr, int* tc);
-cudaError_t launch_conv3x3_tc(const ConvParams& p, const float* w_blocks, int n_slices, const void* tmap_in,
+cudaError_t launch_conv3x3_tc(const ConvParams& p, const float* w_blocks, int n_slices, int w_copies, const void* tmap_in,
                               int sm_count, cudaStream_t s);
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

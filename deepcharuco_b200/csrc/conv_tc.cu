@@ -22,7 +22,7 @@
 // Weights are split offline (engine.cu: pack_tc); activations are converted in shared memory by a dedicated
 // warpgroup, once per halo tile (not once per tap).
 //
-// Data movement.  Activations live in HBM as [n][C/4][H][W][4] fp32.  One TMA box {4, haloW, haloH, 4 groups}
+// Data movement.  Activations live in HBM as [n][C/4][H][W][4] fp32.  One TMA box {4*haloW, haloH, 4 groups}
 // brings a (16*TR+2) x (8*TC+2) pixel halo of 16 input channels into shared memory as planes of 16-byte
 // pixels (4 fp32 channels); the converter rewrites them as fp16 planes of 16-byte pixels (8 channels).  In that
 // layout any run of 8 horizontally adjacent pixels IS a no-swizzle K-major core matrix (8 rows x 16 B),
@@ -49,23 +49,28 @@ namespace dcu {
 namespace {
 
 constexpr int TC_THREADS = 512;
+#ifndef DCU_TC_MT64
+#define DCU_TC_MT64 2
+#endif
 
 template <int NT>
 struct TcCfg {
   // Measured on B200 (profiles/r1_tc_variants.txt): for NT=64, MT=4 single-set beats MT=2 double-buffered (7260 vs 7063
   // frames/s): both are shared-memory-bandwidth bound and MT=4 halves the weight-block fills per MMA.
-  static constexpr int MT = (NT == 64) ? 4 : 2;                 // 128-pixel m-tiles per CTA tile
+  static constexpr int MT = (NT == 64) ? DCU_TC_MT64 : 2;       // 128-pixel m-tiles per CTA tile
   static constexpr int NBUF = 512 / (MT * 2 * NT);              // accumulator sets in TMEM (NBUF * MT * 2*NT = 512 columns)
-  static constexpr int A_STAGES = (NT == 64) ? 2 : 3;
-  static constexpr int B_STAGES = 8;
+  static constexpr int A_STAGES = (NT == 64) ? (MT == 4 ? 2 : 3) : 3;
+  static constexpr int TPB = 3;                                 // taps per weight stage (one bulk copy brings TPB blocks)
+  static constexpr int B_STAGES = (NT == 64) ? 4 : 3;
   static constexpr int MAX_HALO_PX = (MT == 4) ? 18 * 34 : 34 * 10;
   static constexpr int A_RAW_BYTES = 4 * MAX_HALO_PX * 16;      // TMA landing zone: 4 planes of 4 fp32 channels
   static constexpr int A_HALF_BYTES = 2 * MAX_HALO_PX * 16;     // fp16 hi (or lo): 2 planes of 8 channels
   static constexpr int A_STAGE_BYTES = A_RAW_BYTES + 2 * A_HALF_BYTES;   // raw | hi | lo
   static constexpr int B_BLOCK_BYTES = 2 * (2 * NT) * 16;       // 2 k-groups x (NT hi rows + NT lo rows) x 8 fp16
   static constexpr int PARAM_BYTES = 3 * 512 * 4;               // bias / alpha / beta for up to 512 channels
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_BLOCK_BYTES + PARAM_BYTES + BAR_BYTES + 128;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int B_STAGE_BYTES = TPB * B_BLOCK_BYTES;
+  static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + PARAM_BYTES + BAR_BYTES + 128;
 };
 
 struct TcGeo {
@@ -73,6 +78,8 @@ struct TcGeo {
   int halo_w, halo_h;    // 8*tc+2, 16*tr+2
   int tiles_x, tiles_y;
   int slices;            // cout_total / NT
+  int w_copies;          // replicas of the packed weights in HBM (L2 hot-spot avoidance)
+  long long w_copy_bytes;
   long long total_tiles;
 };
 
@@ -104,27 +111,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must fail the launch (trap), never hang the GPU box.
+// kBackoffNs > 0: sleep between polls.  Every poll is a shared-memory transaction, and with 14 of 16 warps waiting most
+// of the time un-throttled polling took ~15 % of the shared-memory data pipe this kernel is bound by (ncu:
+// l1tex__data_pipe_lsu_wavefronts_mem_shared, profiles/r1_conv1b_ncu.txt).  Only the MMA issuer polls without back-off.
+template <int kBackoffNs = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (kBackoffNs > 0) __nanosleep(kBackoffNs);
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 
 // wait + accumulate the cycles spent waiting into *acc (profiling builds of the role loops)
+template <int kBackoffNs = 0>
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
-  if (!timed) { mbar_wait(bar, parity); return; }
+  if (!timed) { mbar_wait<kBackoffNs>(bar, parity); return; }
   const long long t0 = clock64();
-  mbar_wait(bar, parity);
+  mbar_wait<kBackoffNs>(bar, parity);
   acc += clock64() - t0;
 }
 
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -256,7 +268,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   uint8_t* a_smem = smem;
   uint8_t* b_smem = a_smem + Cfg::A_STAGES * Cfg::A_STAGE_BYTES;
-  float* prm = reinterpret_cast<float*>(b_smem + B_STAGES * Cfg::B_BLOCK_BYTES);
+  float* prm = reinterpret_cast<float*>(b_smem + B_STAGES * Cfg::B_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(prm) + Cfg::PARAM_BYTES);
   uint64_t* a_full = bars;                         // [A_STAGES] TMA landed (tx bytes)
   uint64_t* a_ready = a_full + Cfg::A_STAGES;      // [A_STAGES] hi/lo split done (128 arrivals)
@@ -301,9 +313,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
     for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       const TileCoord c = decode_tile(t, g);
       for (int q = 0; q < chunks; ++q) {
-        mbar_wait(&a_empty[st], ph ^ 1u);
+        mbar_wait<200>(&a_empty[st], ph ^ 1u);
         mbar_expect_tx(&a_full[st], (uint32_t)halo_px * 64u);
-        tma_load_5d(smem_u32(a_smem + (size_t)st * Cfg::A_STAGE_BYTES), &tmap, &a_full[st], 0, c.x0 - p.pad, c.y0 - p.pad,
+        tma_load_4d(smem_u32(a_smem + (size_t)st * Cfg::A_STAGE_BYTES), &tmap, &a_full[st], (c.x0 - p.pad) * 4, c.y0 - p.pad,
                     q * 4, c.img);
         if (++st == Cfg::A_STAGES) { st = 0; ph ^= 1u; }
       }
@@ -313,12 +325,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
     int st = 0; uint32_t ph = 0;
     for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       const TileCoord c = decode_tile(t, g);
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(w_blocks) + (size_t)c.slice * chunks * 9 * Cfg::B_BLOCK_BYTES;
-      for (int blk = 0; blk < chunks * 9; ++blk) {
-        mbar_wait(&b_empty[st], ph ^ 1u);
-        mbar_expect_tx(&b_full[st], (uint32_t)Cfg::B_BLOCK_BYTES);
-        bulk_load(smem_u32(b_smem + (size_t)st * Cfg::B_BLOCK_BYTES), wsrc + (size_t)blk * Cfg::B_BLOCK_BYTES,
-                  (uint32_t)Cfg::B_BLOCK_BYTES, &b_full[st]);
+      // every CTA streams the same weight blocks at about the same time: read them from one of g.w_copies replicas so the
+      // requests spread over more L2 slices (and both dies) instead of hammering the few slices that home one copy
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(w_blocks) + (size_t)(blockIdx.x % g.w_copies) * g.w_copy_bytes +
+                            (size_t)c.slice * chunks * 9 * Cfg::B_BLOCK_BYTES;
+      for (int blk = 0; blk < chunks * 9; blk += Cfg::TPB) {
+        mbar_wait<200>(&b_empty[st], ph ^ 1u);
+        mbar_expect_tx(&b_full[st], (uint32_t)Cfg::B_STAGE_BYTES);
+        bulk_load(smem_u32(b_smem + (size_t)st * Cfg::B_STAGE_BYTES), wsrc + (size_t)blk * Cfg::B_BLOCK_BYTES,
+                  (uint32_t)Cfg::B_STAGE_BYTES, &b_full[st]);
         if (++st == B_STAGES) { st = 0; ph ^= 1u; }
       }
     }
@@ -351,11 +366,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
         const uint32_t a_hi = a_desc_lo0 + a_base0 + (uint32_t)sa * (Cfg::A_STAGE_BYTES >> 4) + (uint32_t)(Cfg::A_RAW_BYTES >> 4);
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait_t(&b_full[sb], phb, timed, w_b);
-          tc_fence_after();
           const int ky = tap / 3, kx = tap - 3 * ky;
+          if (kx == 0) {                         // TPB == 3: one weight stage per kernel row
+            mbar_wait_t(&b_full[sb], phb, timed, w_b);
+            tc_fence_after();
+          }
           const uint32_t a_tap = a_hi + (uint32_t)(ky * g.halo_w + kx);
-          const uint32_t b_blk = b_desc_lo0 + b_base0 + (uint32_t)sb * (Cfg::B_BLOCK_BYTES >> 4);
+          const uint32_t b_blk = b_desc_lo0 + b_base0 + (uint32_t)sb * (Cfg::B_STAGE_BYTES >> 4) + (uint32_t)kx * (Cfg::B_BLOCK_BYTES >> 4);
           const bool first = (q | tap) == 0;
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
@@ -370,14 +387,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
               umma_f16_w(d, da_hi, a_desc_hi, b_blk, b_desc_hi, IDESC_2N, first ? 0u : 1u);      // main | a_hi*w_lo
               umma_f16_w(d + NT, da_lo, a_desc_hi, b_blk, b_desc_hi, IDESC_1N, 1u);              // + a_lo*w_hi
               if (mt == MT - 1) {
-                umma_commit(&b_empty[sb]);
+                if (kx == 2) umma_commit(&b_empty[sb]);
                 if (tap == 8) umma_commit(&a_empty[sa]);
                 if (tap == 8 && q == chunks - 1) umma_commit(&acc_full[buf]);
               }
             }
             __syncwarp();
           }
-          if (++sb == B_STAGES) { sb = 0; phb ^= 1u; }
+          if (kx == 2) { if (++sb == B_STAGES) { sb = 0; phb ^= 1u; } }
         }
         if (++sa == Cfg::A_STAGES) { sa = 0; pha ^= 1u; }
       }
@@ -398,7 +415,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
     const long long t_start = clock64();
     for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       for (int q = 0; q < chunks; ++q) {
-        mbar_wait_t(&a_full[st], ph, timed, w_f);
+        mbar_wait_t<100>(&a_full[st], ph, timed, w_f);
         const float4* raw = reinterpret_cast<const float4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES);
         uint4* hi = reinterpret_cast<uint4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES + Cfg::A_RAW_BYTES);
         uint4* lo = reinterpret_cast<uint4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES + Cfg::A_RAW_BYTES + Cfg::A_HALF_BYTES);
@@ -460,7 +477,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
     const long long t_start = clock64();
     for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       const TileCoord c = decode_tile(t, g);
-      mbar_wait_t(&acc_full[buf], phc, timed, w_e);
+      mbar_wait_t<200>(&acc_full[buf], phc, timed, w_e);
       tc_fence_after();
       const int ch_base = c.slice * NT;
 #pragma unroll 1
@@ -564,7 +581,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
 
 // m-tile arrangement (TR x TC tiles of 16 rows x 8 cols) per CTA tile; also sizes the TMA box (engine.cu)
 void tc_tile_arrangement(int nt, int hout, int wout, int* tr, int* tc) {
-  if (nt == 64) {               // MT = 4
+  if (nt == 64 && DCU_TC_MT64 == 4) {
     if (wout >= 32) { *tr = 1; *tc = 4; }
     else if (hout > 16 && wout > 8) { *tr = 2; *tc = 2; }
     else { *tr = 1; *tc = 4; }
@@ -584,8 +601,8 @@ int tc_supported_shape(int cin, int cout) {
 }
 
 template <int NT>
-static cudaError_t launch_nt(const ConvParams& p, const float* w_blocks, int n_slices, const CUtensorMap* tm, int sm_count,
-                             cudaStream_t s) {
+static cudaError_t launch_nt(const ConvParams& p, const float* w_blocks, int n_slices, int w_copies, const CUtensorMap* tm,
+                             int sm_count, cudaStream_t s) {
   using Cfg = TcCfg<NT>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -600,6 +617,8 @@ static cudaError_t launch_nt(const ConvParams& p, const float* w_blocks, int n_s
   if (g.halo_w * g.halo_h > Cfg::MAX_HALO_PX) return cudaErrorInvalidValue;
   g.tiles_x = ceil_div(p.wout, 8 * g.tc); g.tiles_y = ceil_div(p.hout, 16 * g.tr);
   g.slices = n_slices;
+  g.w_copies = w_copies < 1 ? 1 : w_copies;
+  g.w_copy_bytes = (long long)n_slices * (p.cin / 16) * 9 * Cfg::B_BLOCK_BYTES;
   g.total_tiles = (long long)p.n * g.slices * g.tiles_x * g.tiles_y;
   if (g.total_tiles <= 0) return cudaSuccess;
   const int grid = (int)(g.total_tiles < sm_count ? g.total_tiles : sm_count);
@@ -607,12 +626,12 @@ static cudaError_t launch_nt(const ConvParams& p, const float* w_blocks, int n_s
   return cudaGetLastError();
 }
 
-cudaError_t launch_conv3x3_tc(const ConvParams& p, const float* w_blocks, int n_slices, const void* tmap_in, int sm_count,
-                              cudaStream_t s) {
+cudaError_t launch_conv3x3_tc(const ConvParams& p, const float* w_blocks, int n_slices, int w_copies, const void* tmap_in,
+                              int sm_count, cudaStream_t s) {
   const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(tmap_in);
   const int nt = tc_supported_shape(p.cin, p.cout_total);
-  if (nt == 64) return launch_nt<64>(p, w_blocks, n_slices, tm, sm_count, s);
-  if (nt == 128) return launch_nt<128>(p, w_blocks, n_slices, tm, sm_count, s);
+  if (nt == 64) return launch_nt<64>(p, w_blocks, n_slices, w_copies, tm, sm_count, s);
+  if (nt == 128) return launch_nt<128>(p, w_blocks, n_slices, w_copies, tm, sm_count, s);
   return cudaErrorInvalidValue;
 }
 

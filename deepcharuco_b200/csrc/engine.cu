@@ -49,6 +49,7 @@ struct Layer3x3 {
   DevBuf w_ffma;              // [cin/4][9][4][cout]
   DevBuf w_tc;                // tcgen05 blocks (conv_tc.cu layout), empty if shape unsupported
   float tc_scale = 1.f;       // power-of-two weight scale baked into w_tc
+  int tc_copies = 1;          // replicas of w_tc (spread the all-CTA broadcast reads over more L2 slices)
   int tc_nt = 0;              // N per CTA pass for the tcgen05 kernel (64 / 128), 0 = unsupported
   DevBuf bias, alpha, beta;   // [cout]
 };
@@ -259,8 +260,11 @@ int build_3x3(Layer3x3& l, std::vector<const DcuConvLayer*> parts, int pad, int 
   if (l.tc_nt > 0) {
     l.tc_scale = tc_weight_scale(ws, couts, cin);
     const std::vector<uint16_t> blocks = pack_tc(ws, couts, cin, l.tc_nt, l.tc_scale);
-    CK(l.w_tc.alloc(blocks.size() * 2));
-    CK(cudaMemcpy(l.w_tc.p, blocks.data(), blocks.size() * 2, cudaMemcpyHostToDevice));
+    l.tc_copies = 8;
+    if (const char* v = getenv("DCU_W_COPIES")) l.tc_copies = std::max(1, atoi(v));
+    CK(l.w_tc.alloc(blocks.size() * 2 * l.tc_copies));
+    for (int c = 0; c < l.tc_copies; ++c)
+      CK(cudaMemcpy(l.w_tc.as<uint8_t>() + (size_t)c * blocks.size() * 2, blocks.data(), blocks.size() * 2, cudaMemcpyHostToDevice));
   }
   return DCU_OK;
 }
@@ -273,11 +277,14 @@ int build_3x3(Layer3x3& l, std::vector<const DcuConvLayer*> parts, int pad, int 
 static int make_tmap(CUtensorMap* tm, const float* base, int n, int cin, int h, int w, int box_w, int box_h) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[5] = {4, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)(cin / 4), (cuuint64_t)n};
-  cuuint64_t strides[4] = {16, (cuuint64_t)w * 16, (cuuint64_t)w * h * 16, (cuuint64_t)w * h * 16 * (cin / 4)};
-  cuuint32_t box[5] = {4, (cuuint32_t)box_w, (cuuint32_t)box_h, 4, 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+  // [n][cin/4][h][w][4 floats] viewed as a 4-D tensor whose innermost dimension is a whole image row of 16-byte pixels
+  // (w*4 floats): the box row is then halo_w*16 contiguous bytes instead of 16, which is what the TMA engine moves
+  // efficiently; the shared-memory image is the same (planes of halo_h x halo_w 16-byte pixels).
+  cuuint64_t dims[4] = {(cuuint64_t)w * 4, (cuuint64_t)h, (cuuint64_t)(cin / 4), (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)w * 16, (cuuint64_t)w * h * 16, (cuuint64_t)w * h * 16 * (cin / 4)};
+  cuuint32_t box[4] = {(cuuint32_t)box_w * 4, (cuuint32_t)box_h, 4, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
@@ -304,7 +311,7 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
     CUtensorMap tm;
     int rc = make_tmap(&tm, in, n, l.cin, hin, win, 8 * g.tc + 2, 16 * g.tr + 2);
     if (rc) return rc;
-    cudaError_t ce = launch_conv3x3_tc(p, l.w_tc.as<float>(), l.cout / l.tc_nt, &tm, e->sm_count, s);
+    cudaError_t ce = launch_conv3x3_tc(p, l.w_tc.as<float>(), l.cout / l.tc_nt, l.tc_copies, &tm, e->sm_count, s);
     if (ce != cudaSuccess) return fail(DCU_ERR_CUDA, std::string("tcgen05 conv launch: ") + cudaGetErrorString(ce));
   } else {
     launch_conv3x3_ffma(p, l.w_ffma.as<float>(), s);
