@@ -55,8 +55,8 @@ constexpr int TC_THREADS = 512;
 
 template <int NT>
 struct TcCfg {
-  // Measured on B200 (profiles/r1_tc_variants.txt): for NT=64, MT=4 single-set beats MT=2 double-buffered (7260 vs 7063
-  // frames/s): both are shared-memory-bandwidth bound and MT=4 halves the weight-block fills per MMA.
+  // NT=64: MT=2 with a double-buffered accumulator set (epilogue fully overlapped) and MT=4 with a single set measure
+  // the same on B200 (profiles/r1_tc_variants.txt); MT=2 is the default, -DDCU_TC_MT64=4 builds the other.
   static constexpr int MT = (NT == 64) ? DCU_TC_MT64 : 2;       // 128-pixel m-tiles per CTA tile
   static constexpr int NBUF = 512 / (MT * 2 * NT);              // accumulator sets in TMEM (NBUF * MT * 2*NT = 512 columns)
   static constexpr int A_STAGES = (NT == 64) ? (MT == 4 ? 2 : 3) : 3;
@@ -178,32 +178,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -219,23 +193,6 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t ta, float* a, uint32_t tb, 
   tmem_ld16_nowait(tb, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// two 32-column loads in flight, one wait
-__device__ __forceinline__ void tmem_ld32x2(uint32_t ta, float* a, uint32_t tb, float* b) {
-  tmem_ld32_nowait(ta, a);
-  tmem_ld32_nowait(tb, b);
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-
 __device__ __forceinline__ unsigned int orderable(float v) {
   unsigned int b = __float_as_uint(v);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -283,7 +240,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
   const int lane = threadIdx.x & 31;
   const int chunks = p.cin >> 4;
   const int halo_px = g.halo_w * g.halo_h;
-  const uint32_t plane = (uint32_t)halo_px * 16u;
 
   for (int i = threadIdx.x; i < p.cout_total; i += TC_THREADS) {
     prm[i] = p.bias[i];
