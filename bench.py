@@ -249,11 +249,11 @@ def main():
     dec_bytes += 2 * (total_k * (2304 + 2304 + 16))          # + K*(patch read + patch write + record), 2 profiled steps
 
     if rank == 0:
-        impl_name = {Nn.CONV_FFMA: "ffma-fp32", Nn.CONV_TCGEN05: "tcgen05-3xtf32"}[eng.conv_impl]
+        impl_name = {Nn.CONV_FFMA: "ffma-fp32", Nn.CONV_TCGEN05: "tcgen05-f16-hi/lo-split(3 products, fp32 accumulate)"}[eng.conv_impl]
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-            dtype="f32" if eng.conv_impl == Nn.CONV_FFMA else "tf32x3(f32-equivalent)", data="synthetic",
+            dtype="f32" if eng.conv_impl == Nn.CONV_FFMA else "f16x2-split(f32-equivalent)", data="synthetic",
             config=dict(workload=f"batch={B} 320x240 frames per GPU, full pipeline (detector + decode + RefineNet)",
                         frames_per_gpu_per_step=B, corners_per_step_rank0=total_k, conv_impl=impl_name,
                         weights="trained reference checkpoints (converted .npz)",

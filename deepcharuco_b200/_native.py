@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("DCU_LIB_PATH") or os.path.join(_HERE, "libdeepcharuco
 
 DCU_OK, DCU_ERR_INVALID, DCU_ERR_CUDA, DCU_ERR_CAPACITY, DCU_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 CONV_FFMA, CONV_TCGEN05 = 0, 1
-CONV_DEFAULT = CONV_TCGEN05   # tcgen05 3xTF32 tensor-core path; CONV_FFMA is the strict-fp32 CUDA-core path
+CONV_DEFAULT = CONV_TCGEN05   # tcgen05 tensor-core path (fp16 hi/lo split); CONV_FFMA is the strict-fp32 CUDA-core path
 
 EXPORTS = [
     "dcu_create", "dcu_destroy", "dcu_detector_forward", "dcu_detector_forward_f32", "dcu_extract_patches",

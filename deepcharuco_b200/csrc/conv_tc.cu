@@ -221,9 +221,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
   constexpr int MT = Cfg::MT;
   constexpr int NBUF = Cfg::NBUF;
   constexpr int B_STAGES = Cfg::B_STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  uint8_t* a_smem = smem;
+  // NB: no integer round-trip on this pointer -- it would demote every shared-memory access below to a generic LD/ST
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* a_smem = smem_raw;
   uint8_t* b_smem = a_smem + Cfg::A_STAGES * Cfg::A_STAGE_BYTES;
   float* prm = reinterpret_cast<float*>(b_smem + B_STAGES * Cfg::B_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(prm) + Cfg::PARAM_BYTES);

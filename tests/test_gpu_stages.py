@@ -12,7 +12,10 @@ from deepcharuco_b200 import _native as N
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL = 2e-3      # |delta| on logits of magnitude ~1e2 for an fp32 path with a different summation order
+# |delta| on logits of magnitude ~1e2.  fp32 CUDA-core path: a different summation order only.  tcgen05 path: the fp16
+# hi/lo split keeps 22 bits per operand but the tensor core's fp32 accumulation truncates once per MMA, which through
+# ten layers shows up as ~5e-4 relative on the logits (measured max 0.1 on 128 frames; tools/parity_report.py).
+LOGIT_TOL = {N.CONV_FFMA: 5e-3, N.CONV_TCGEN05: 0.25}
 HEAT_TOL = 5e-5       # |delta| on the 64x64 heat map (range ~[0,1])
 
 
@@ -27,19 +30,25 @@ def engine(states):
     e.close()
 
 
-def test_detector_logits(engine, golden_synth):
+@pytest.mark.parametrize("impl", [N.CONV_FFMA, N.CONV_TCGEN05])
+def test_detector_logits(engine, golden_synth, impl):
     g = golden_synth
+    engine.set_conv_impl(impl)
     n = g["loc"].shape[0]
     frames = _cuda(g["frames"][:n])
     loc = torch.empty((n, 65, 30, 40), device="cuda")
     ids = torch.empty((n, 17, 30, 40), device="cuda")
     N.check(N.lib().dcu_detector_forward(engine.handle, frames.data_ptr(), n, loc.data_ptr(), ids.data_ptr(), None))
     torch.cuda.synchronize()
+    engine.set_conv_impl(N.CONV_DEFAULT)
     dl = (loc.cpu().numpy() - g["loc"])
     di = (ids.cpu().numpy() - g["ids"])
-    assert np.abs(dl).max() < LOGIT_TOL and np.abs(di).max() < LOGIT_TOL, (np.abs(dl).max(), np.abs(di).max())
-    assert np.array_equal(loc.cpu().numpy().argmax(1), g["loc"].argmax(1)) or np.abs(dl).max() < LOGIT_TOL
+    tol = LOGIT_TOL[impl]
+    assert np.abs(dl).max() < tol and np.abs(di).max() < tol, (np.abs(dl).max(), np.abs(di).max())
+    # what the decode consumes: the per-cell arg-max of ids, and of loc on every cell the reference keeps
     assert np.array_equal(ids.cpu().numpy().argmax(1), g["ids"].argmax(1))
+    kept = (g["loc"].argmax(1) != 64) & (g["ids"].argmax(1) != 16)
+    assert np.array_equal(loc.cpu().numpy().argmax(1)[kept], g["loc"].argmax(1)[kept])
 
 
 def test_detector_f32_entry_equals_u8_entry(engine, golden_synth):

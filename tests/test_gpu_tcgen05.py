@@ -1,4 +1,4 @@
-"""The tcgen05 (3xTF32) convolution path: per layer against the fp32 CUDA-core kernel and the oracle, then the
+"""The tcgen05 (fp16 hi/lo split, 3 products) convolution path: per layer against the fp32 CUDA-core kernel and the oracle, then the
 whole pipeline against the golden fixtures and the oracle.  Runs last (a kernel fault poisons the CUDA context)."""
 import numpy as np
 import pytest
@@ -50,7 +50,7 @@ def test_layer_tcgen05_matches_fp32_kernel(engine, shape):
         outs.append(out.cpu().numpy())
     a, b = outs
     assert not np.isnan(b).any()
-    # 3xTF32 keeps ~22 mantissa bits per operand: agreement with the fp32 FMA kernel at fp32-noise level
+    # the fp16 hi/lo split keeps ~22 bits per operand: agreement with the fp32 FMA kernel at fp32-noise level
     assert np.abs(a - b).max() <= 2e-5 * max(1.0, np.abs(a).max()), np.abs(a - b).max()
 
 

@@ -36,7 +36,7 @@ orc = [oracle.pipeline.infer_gray(states[0], states[1], f, return_stages=True) f
 t_or = time.time() - t0
 report = dict(frames=a.frames, seed=a.seed, oracle_seconds=t_or, torch=torch.__version__, impls={})
 deepc, refinenet = dc.load_models(dc.DEFAULT_DEEPC, dc.DEFAULT_REFINENET, 16, "cuda:0")
-for name, impl in (("tcgen05_3xtf32", N.CONV_TCGEN05), ("ffma_fp32", N.CONV_FFMA)):
+for name, impl in (("tcgen05_f16x2", N.CONV_TCGEN05), ("ffma_fp32", N.CONV_FFMA)):
     deepc._ctx.set_conv_impl(impl)
     refined = dc.infer_batch(frames, 16, deepc, refinenet)
     raw = dc.infer_batch(frames, 16, deepc, None)
