@@ -1,9 +1,13 @@
 // Shared declarations for the deepcharuco_b200 CUDA sources (sm_100a only).
 //
-// Activation layout in HBM ("C4"): float [n][C/4][H][W][4] -- channels in groups of four, each group
-// a plane of float4 pixels.  Chosen for Blackwell: a TMA box {4, w, h, groups} of this tensor lands
-// in shared memory as the no-swizzle K-major core-matrix layout tcgen05.mma reads (8 pixels x 16 B
-// contiguous), at ANY pixel offset, so one halo tile serves all nine taps of a 3x3 convolution.
+// Activation layouts in HBM.  Both keep "planes of 16-byte pixels", so that a TMA box of a plane lands in shared memory
+// as the no-swizzle K-major core-matrix layout tcgen05.mma reads (8 horizontally adjacent pixels x 16 B), at ANY pixel
+// offset, and one halo tile serves all nine taps of a 3x3 convolution.
+//   "C4" (fp32 CUDA-core path):  float  [n][C/4][H][W][4]      -- 4 fp32 channels per 16-byte pixel
+//   "H2" (tcgen05 path):         __half [n][2][C/8][H][W][8]   -- index 0: x_hi = fp16(x), index 1: x_lo = fp16(x - x_hi);
+//        8 fp16 channels per 16-byte pixel.  Same bytes per element as fp32 (2 + 2), 22 significant bits, and it is
+//        exactly the operand pair the split-precision MMA consumes, so the consumer needs no conversion pass: the
+//        producing kernel's epilogue does the split once per element.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -46,7 +50,8 @@ struct FirstConvParams {
   const uint8_t* in_u8;   // [n][hin][win] or null
   const float* in_f32;    // [n][hin][win] or null
   const float* lut;       // [256] fp32 (x-128)/255, host-computed (model_utils.py:46-50)
-  float* out;             // C4 [n][16][hout][wout][4]
+  float* out;             // C4 [n][16][hout][wout][4], or H2 [n][2][8][hout][wout][8] fp16 when out_h2 != 0
+  int out_h2;
   const float* w;         // [9][64]
   const float* bias; const float* alpha; const float* beta;   // [64]
   int n, hin, win, hout, wout, pad;
@@ -55,7 +60,8 @@ void launch_conv_first(const FirstConvParams& p, cudaStream_t s);
 
 // 1x1 heads of the detector (convPb 256->65, convDb 256->n_ids+1), NCHW outputs (net.py:74,77)
 struct HeadParams {
-  const float* in;        // C4 [n][128][h][w][4]: channels 0..255 = cPa, 256..511 = cDa
+  const float* in;        // C4 [n][128][h][w][4] (or H2 [n][2][64][h][w][8] fp16 when in_h2 != 0): channels 0..255 = cPa, 256..511 = cDa
+  int in_h2;
   const float* w_loc;     // [65][256]
   const float* b_loc;     // [65]
   const float* w_ids;     // [n_ids+1][256]
@@ -88,6 +94,8 @@ void launch_refine_finalize(const unsigned long long* keys, const int32_t* xy, i
 // layout converters used by the debug/test entry point
 void launch_nchw_to_c4(const float* in, float* out, int n, int c, int h, int w, cudaStream_t s);
 void launch_c4_to_nchw(const float* in, float* out, int n, int c, int h, int w, cudaStream_t s);
+void launch_nchw_to_h2(const float* in, void* out, int n, int c, int h, int w, cudaStream_t s);
+void launch_h2_to_nchw(const void* in, float* out, int n, int c, int h, int w, cudaStream_t s);
 
 // tcgen05 path (conv_tc.cu)
 struct TcLayerPack {

@@ -8,6 +8,8 @@
 //   convPb 1x1 + flat arg-max (first max wins)  refinenet.py:81,111; model_utils.py:39-43
 // The accumulation is plain fp32 FMA (no tensor cores): this is the strict-fp32 path and the on-GPU
 // cross-check for the tcgen05 path in conv_tc.cu.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace dcu {
@@ -28,6 +30,16 @@ __device__ __forceinline__ float bn_relu(float acc, float bias, float alpha, flo
   // relu(fma(acc + bias, alpha, beta)): reproduces ATen's eval BatchNorm2d bit-for-bit given the same
   // conv output; conv bias is added first, as F.conv2d does.
   return fmaxf(fmaf(acc + bias, alpha, beta), 0.0f);
+}
+
+// x -> (fp16(x), fp16(x - fp16(x))) for two values at once; inputs are post-ReLU (>= 0), clamped to fp16's finite range
+__device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  x0 = fminf(x0, 65504.f); x1 = fminf(x1, 65504.f);
+  const __half2 hh = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
 }
 
 // monotone map float -> uint32 (larger float => larger key); used for the packed arg-max key
@@ -274,19 +286,37 @@ conv_first_kernel(FirstConvParams p, long long total_px) {
         v[ky * 3 + kx] = x;
       }
     float4* outp = reinterpret_cast<float4*>(p.out);
-#pragma unroll 4
-    for (int g = 0; g < 16; ++g) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    uint4* outh = reinterpret_cast<uint4*>(p.out);
+    const size_t plane = (size_t)p.hout * p.wout;
+#pragma unroll 2
+    for (int g8 = 0; g8 < 8; ++g8) {          // 8 output channels per iteration
+      float y[8];
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const float4 w = *reinterpret_cast<const float4*>(&w_s[tap * 64 + g * 4]);
-        a0 = fmaf(v[tap], w.x, a0); a1 = fmaf(v[tap], w.y, a1);
-        a2 = fmaf(v[tap], w.z, a2); a3 = fmaf(v[tap], w.w, a3);
+      for (int half = 0; half < 2; ++half) {
+        const int c = g8 * 8 + half * 4;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const float4 w = *reinterpret_cast<const float4*>(&w_s[tap * 64 + c]);
+          a0 = fmaf(v[tap], w.x, a0); a1 = fmaf(v[tap], w.y, a1);
+          a2 = fmaf(v[tap], w.z, a2); a3 = fmaf(v[tap], w.w, a3);
+        }
+        y[half * 4 + 0] = bn_relu(a0, bi_s[c], al_s[c], be_s[c]);
+        y[half * 4 + 1] = bn_relu(a1, bi_s[c + 1], al_s[c + 1], be_s[c + 1]);
+        y[half * 4 + 2] = bn_relu(a2, bi_s[c + 2], al_s[c + 2], be_s[c + 2]);
+        y[half * 4 + 3] = bn_relu(a3, bi_s[c + 3], al_s[c + 3], be_s[c + 3]);
       }
-      const int c = g * 4;
-      outp[(((size_t)img * 16 + g) * p.hout + oy) * p.wout + ox] =
-          make_float4(bn_relu(a0, bi_s[c], al_s[c], be_s[c]), bn_relu(a1, bi_s[c + 1], al_s[c + 1], be_s[c + 1]),
-                      bn_relu(a2, bi_s[c + 2], al_s[c + 2], be_s[c + 2]), bn_relu(a3, bi_s[c + 3], al_s[c + 3], be_s[c + 3]));
+      if (p.out_h2) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_h2(y[2 * e], y[2 * e + 1], h[e], l[e]);
+        const size_t pix = (size_t)oy * p.wout + ox;
+        outh[((size_t)img * 2 * 8 + g8) * plane + pix] = make_uint4(h[0], h[1], h[2], h[3]);
+        outh[((size_t)img * 2 * 8 + 8 + g8) * plane + pix] = make_uint4(l[0], l[1], l[2], l[3]);
+      } else {
+        outp[(((size_t)img * 16 + 2 * g8) * p.hout + oy) * p.wout + ox] = make_float4(y[0], y[1], y[2], y[3]);
+        outp[(((size_t)img * 16 + 2 * g8 + 1) * p.hout + oy) * p.wout + ox] = make_float4(y[4], y[5], y[6], y[7]);
+      }
     }
   }
 }
@@ -312,12 +342,33 @@ heads_1x1_kernel(HeadParams p, int cells_per_img, int blocks_per_img) {
   const int img = blockIdx.x / blocks_per_img;
   const int cell0 = (blockIdx.x % blocks_per_img) * H_CELLS;
   const int tid = threadIdx.x;
-  const float4* src = reinterpret_cast<const float4*>(p.in) + (size_t)img * 128 * cells_per_img;
-  for (int i = tid; i < 128 * H_CELLS; i += 128) {
-    const int g = i / H_CELLS, c = i % H_CELLS;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (cell0 + c < cells_per_img) v = src[(size_t)g * cells_per_img + cell0 + c];
-    in_s[4 * g + 0][c] = v.x; in_s[4 * g + 1][c] = v.y; in_s[4 * g + 2][c] = v.z; in_s[4 * g + 3][c] = v.w;
+  if (p.in_h2) {
+    // H2: [img][hi|lo][64 groups of 8][cells][8 fp16]; x = hi + lo (22 significant bits)
+    const uint4* src = reinterpret_cast<const uint4*>(p.in) + (size_t)img * 2 * 64 * cells_per_img;
+    for (int i = tid; i < 64 * H_CELLS; i += 128) {
+      const int g = i / H_CELLS, c = i % H_CELLS;
+      uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
+      if (cell0 + c < cells_per_img) {
+        h = src[(size_t)g * cells_per_img + cell0 + c];
+        l = src[(size_t)(64 + g) * cells_per_img + cell0 + c];
+      }
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+        in_s[8 * g + 2 * e][c] = a.x + b.x;
+        in_s[8 * g + 2 * e + 1][c] = a.y + b.y;
+      }
+    }
+  } else {
+    const float4* src = reinterpret_cast<const float4*>(p.in) + (size_t)img * 128 * cells_per_img;
+    for (int i = tid; i < 128 * H_CELLS; i += 128) {
+      const int g = i / H_CELLS, c = i % H_CELLS;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cell0 + c < cells_per_img) v = src[(size_t)g * cells_per_img + cell0 + c];
+      in_s[4 * g + 0][c] = v.x; in_s[4 * g + 1][c] = v.y; in_s[4 * g + 2][c] = v.z; in_s[4 * g + 3][c] = v.w;
+    }
   }
   __syncthreads();
   const int cell = tid % H_CELLS, og = tid / H_CELLS;   // og 0..7
@@ -404,6 +455,43 @@ __global__ void c4_to_nchw_kernel(const float* in, float* out, int n, int c, int
     out[i] = in[((((size_t)img * (c >> 2) + (ch >> 2)) * h + y) * w + x) * 4 + (ch & 3)];
   }
 }
+__global__ void nchw_to_h2_kernel(const float* in, __half* out, int n, int c, int h, int w) {
+  const long long total = (long long)n * c * h * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w); long long t = i / w;
+    const int y = (int)(t % h); t /= h;
+    const int ch = (int)(t % c); const int img = (int)(t / c);
+    const float v = fminf(in[i], 65504.f);
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    const size_t o = ((((size_t)img * 2) * (c >> 3) + (ch >> 3)) * h + y) * w + x;
+    out[o * 8 + (ch & 7)] = hi;
+    out[(o + (size_t)(c >> 3) * h * w) * 8 + (ch & 7)] = lo;
+  }
+}
+__global__ void h2_to_nchw_kernel(const __half* in, float* out, int n, int c, int h, int w) {
+  const long long total = (long long)n * c * h * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w); long long t = i / w;
+    const int y = (int)(t % h); t /= h;
+    const int ch = (int)(t % c); const int img = (int)(t / c);
+    const size_t o = ((((size_t)img * 2) * (c >> 3) + (ch >> 3)) * h + y) * w + x;
+    out[i] = __half2float(in[o * 8 + (ch & 7)]) + __half2float(in[(o + (size_t)(c >> 3) * h * w) * 8 + (ch & 7)]);
+  }
+}
+void launch_nchw_to_h2(const float* in, void* out, int n, int c, int h, int w, cudaStream_t s) {
+  const long long total = (long long)n * c * h * w;
+  if (total <= 0) return;
+  long long b = (total + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+  nchw_to_h2_kernel<<<(int)b, 256, 0, s>>>(in, reinterpret_cast<__half*>(out), n, c, h, w);
+}
+void launch_h2_to_nchw(const void* in, float* out, int n, int c, int h, int w, cudaStream_t s) {
+  const long long total = (long long)n * c * h * w;
+  if (total <= 0) return;
+  long long b = (total + 255) / 256; if (b > 148 * 16) b = 148 * 16;
+  h2_to_nchw_kernel<<<(int)b, 256, 0, s>>>(reinterpret_cast<const __half*>(in), out, n, c, h, w);
+}
+
 void launch_nchw_to_c4(const float* in, float* out, int n, int c, int h, int w, cudaStream_t s) {
   const long long total = (long long)n * c * h * w;
   if (total <= 0) return;

@@ -18,27 +18,27 @@
 // adjacent in the block) and  a_lo x w_hi  (N = NT, into the right half).  Each m-tile therefore owns 2*NT TMEM
 // columns: the left half accumulates the main term, the right half the two small terms; the epilogue adds them
 // in fp32.  This keeps the small terms out of the main accumulator (the hardware accumulation truncates once per
-// MMA) and reads a_hi from shared memory once for both weight halves -- the kernel is shared-memory-bandwidth bound.
-// Weights are split offline (engine.cu: pack_tc); activations are converted in shared memory by a dedicated
-// warpgroup, once per halo tile (not once per tap).
+// MMA) and reads a_hi from shared memory once for both weight halves.
 //
-// Data movement.  Activations live in HBM as [n][C/4][H][W][4] fp32.  One TMA box {4*haloW, haloH, 4 groups}
-// brings a (16*TR+2) x (8*TC+2) pixel halo of 16 input channels into shared memory as planes of 16-byte
-// pixels (4 fp32 channels); the converter rewrites them as fp16 planes of 16-byte pixels (8 channels).  In that
-// layout any run of 8 horizontally adjacent pixels IS a no-swizzle K-major core matrix (8 rows x 16 B),
-// consecutive image rows are SBO = haloW*16 B apart and the next 8 channels are LBO = plane bytes apart -- so all nine taps of the convolution are just nine different descriptor start addresses into
-// the same halo tile: no im2col copy, each input element is fetched from L2 once per tile (+halo).
-// Zero padding comes from TMA out-of-bounds fill.  Weight blocks (pre-packed, hi|lo) arrive by 1-D bulk copy.
+// Data movement.  Activations live in HBM already split ("H2": __half [n][hi|lo][C/8][H][W][8], common.cuh); the
+// producing kernel's epilogue does the split.  One 5-D TMA box {8*haloW, haloH, 2 k-groups, hi|lo} brings a
+// (16*TR+2) x (8*TC+2) pixel halo of 16 input channels into shared memory as four planes of 16-byte pixels.  In
+// that layout any run of 8 horizontally adjacent pixels IS a no-swizzle K-major core matrix (8 rows x 16 B),
+// consecutive image rows are SBO = haloW*16 B apart and the next 8 channels are LBO = plane bytes apart -- so all
+// nine taps of the convolution are nine descriptor start addresses into the same halo tile: no im2col copy, no
+// conversion pass, each input element is fetched from L2 once per tile (+halo); zero padding comes from TMA
+// out-of-bounds fill.  Weight blocks (pre-packed, three taps per stage) arrive by 1-D bulk copy.
+// The kernel is bound by the shared-memory data pipe (operand fetches of the tensor core + fills), not by HBM or
+// the tensor pipe (profiles/r1_ncu_conv3x3_tc.txt), which is why every byte of fill traffic was removed that could be.
 //
-// Roles (512 threads, one persistent CTA per SM).  TMEM: 512 columns = NBUF sets x MT=2 m-tiles x (main | small) x NT
+// Roles (384 threads, one persistent CTA per SM).  TMEM: 512 columns = NBUF sets x MT=2 m-tiles x (main | small) x NT
 // columns; NT=64 double-buffers the set (epilogue of tile i overlaps the MMAs of tile i+1), NT=128 has one set that is
 // handed back to the MMA issuer per m-tile as the epilogue drains it:
-//   warp 0      TMA producer for activation halo chunks          (a_empty -> a_full)
-//   warp 1      tcgen05.mma issuer: warp-uniform loop, one elected lane issues (a_ready, b_full -> commits)
-//   warp 2      TMEM alloc/dealloc + bulk-copy producer for weight blocks (b_empty -> b_full)
-//   warps 4-7, 12-15  epilogue, two groups (even / odd m-tiles): tcgen05.ld -> main+small -> bias/BN/ReLU ->
-//               pool | upsample | head -> global   (acc_full -> acc_empty[mt])
-//   warps 8-11  hi/lo converter: raw fp32 halo planes -> fp16 hi planes + fp16 lo planes  (a_full -> a_ready)
+//   warp 0      TMA producer for activation halo chunks                   (a_empty -> a_full)
+//   warp 1      tcgen05.mma issuer: warp-uniform loop, one elected lane   (a_full, b_full -> commits)
+//   warp 2      TMEM alloc/dealloc + bulk-copy producer for weight stages (b_empty -> b_full)
+//   warps 4-7, 8-11  epilogue, two groups (even / odd m-tiles): tcgen05.ld -> main+small -> *2^-s -> bias/BN/ReLU ->
+//               pool | upsample | head -> hi/lo split -> global           (acc_full -> acc_empty[mt])
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -48,29 +48,22 @@ namespace dcu {
 
 namespace {
 
-constexpr int TC_THREADS = 512;
-#ifndef DCU_TC_MT64
-#define DCU_TC_MT64 2
-#endif
+constexpr int TC_THREADS = 384;
 
 template <int NT>
 struct TcCfg {
-  // NT=64: MT=2 with a double-buffered accumulator set (epilogue fully overlapped) and MT=4 with a single set measure
-  // the same on B200 (profiles/r1_tc_variants.txt); MT=2 is the default, -DDCU_TC_MT64=4 builds the other.
-  static constexpr int MT = (NT == 64) ? DCU_TC_MT64 : 2;       // 128-pixel m-tiles per CTA tile
+  static constexpr int MT = 2;                                  // 128-pixel m-tiles per CTA tile (16x16 or 32x8 pixels)
   static constexpr int NBUF = 512 / (MT * 2 * NT);              // accumulator sets in TMEM (NBUF * MT * 2*NT = 512 columns)
-  static constexpr int A_STAGES = (NT == 64) ? (MT == 4 ? 2 : 3) : 3;
+  static constexpr int A_STAGES = 4;
   static constexpr int TPB = 3;                                 // taps per weight stage (one bulk copy brings TPB blocks)
-  static constexpr int B_STAGES = (NT == 64) ? 4 : 3;
-  static constexpr int MAX_HALO_PX = (MT == 4) ? 18 * 34 : 34 * 10;
-  static constexpr int A_RAW_BYTES = 4 * MAX_HALO_PX * 16;      // TMA landing zone: 4 planes of 4 fp32 channels
-  static constexpr int A_HALF_BYTES = 2 * MAX_HALO_PX * 16;     // fp16 hi (or lo): 2 planes of 8 channels
-  static constexpr int A_STAGE_BYTES = A_RAW_BYTES + 2 * A_HALF_BYTES;   // raw | hi | lo
+  static constexpr int B_STAGES = (NT == 64) ? 6 : 4;
+  static constexpr int MAX_HALO_PX = 34 * 10;                   // 2x1 arrangement; 1x2 is 18 x 18 = 324
+  static constexpr int A_STAGE_BYTES = 4 * MAX_HALO_PX * 16;    // hi (2 planes of 8 channels) | lo (2 planes)
   static constexpr int B_BLOCK_BYTES = 2 * (2 * NT) * 16;       // 2 k-groups x (NT hi rows + NT lo rows) x 8 fp16
+  static constexpr int B_STAGE_BYTES = TPB * B_BLOCK_BYTES;
   static constexpr int PARAM_BYTES = 3 * 512 * 4;               // bias / alpha / beta for up to 512 channels
   static constexpr int BAR_BYTES = 512;
-  static constexpr int B_STAGE_BYTES = TPB * B_BLOCK_BYTES;
-  static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + PARAM_BYTES + BAR_BYTES + 128;
+  static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
 };
 
 struct TcGeo {
@@ -133,10 +126,11 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool
   acc += clock64() - t0;
 }
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -193,6 +187,27 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t ta, float* a, uint32_t tb, 
   tmem_ld16_nowait(tb, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// x -> (fp16(x), fp16(x - fp16(x))) for two values; the inputs are post-ReLU (>= 0) and clamped to fp16's finite range
+__device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  x0 = fminf(x0, 65504.f); x1 = fminf(x1, 65504.f);
+  const __half2 hh = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
+// 16 fp32 channel values of one pixel -> two hi and two lo 16-byte H2 pixels (k-groups kg0, kg0+1)
+__device__ __forceinline__ void store_h2_16(uint4* hi_plane0, size_t lo_offset, size_t kg_stride, const float* v) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_h2(v[8 * k + 2 * e], v[8 * k + 2 * e + 1], h[e], l[e]);
+    hi_plane0[(size_t)k * kg_stride] = make_uint4(h[0], h[1], h[2], h[3]);
+    hi_plane0[(size_t)k * kg_stride + lo_offset] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
 __device__ __forceinline__ unsigned int orderable(float v) {
   unsigned int b = __float_as_uint(v);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -228,8 +243,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
   float* prm = reinterpret_cast<float*>(b_smem + B_STAGES * Cfg::B_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(prm) + Cfg::PARAM_BYTES);
   uint64_t* a_full = bars;                         // [A_STAGES] TMA landed (tx bytes)
-  uint64_t* a_ready = a_full + Cfg::A_STAGES;      // [A_STAGES] hi/lo split done (128 arrivals)
-  uint64_t* a_empty = a_ready + Cfg::A_STAGES;     // [A_STAGES] MMAs reading the stage retired
+  uint64_t* a_empty = a_full + Cfg::A_STAGES;      // [A_STAGES] MMAs reading the stage retired
   uint64_t* b_full = a_empty + Cfg::A_STAGES;      // [B_STAGES]
   uint64_t* b_empty = b_full + B_STAGES;           // [B_STAGES]
   uint64_t* acc_full = b_empty + B_STAGES;         // [NBUF]     all MMAs of the tile retired
@@ -247,7 +261,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
     prm[1024 + i] = p.beta[i];
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < Cfg::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 128); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < Cfg::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < NBUF; ++i) mbar_init(&acc_full[i], 1);
     for (int i = 0; i < NBUF * MT; ++i) mbar_init(&acc_empty[i], 128);
@@ -271,8 +285,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
       for (int q = 0; q < chunks; ++q) {
         mbar_wait<200>(&a_empty[st], ph ^ 1u);
         mbar_expect_tx(&a_full[st], (uint32_t)halo_px * 64u);
-        tma_load_4d(smem_u32(a_smem + (size_t)st * Cfg::A_STAGE_BYTES), &tmap, &a_full[st], (c.x0 - p.pad) * 4, c.y0 - p.pad,
-                    q * 4, c.img);
+        tma_load_5d(smem_u32(a_smem + (size_t)st * Cfg::A_STAGE_BYTES), &tmap, &a_full[st], (c.x0 - p.pad) * 8, c.y0 - p.pad,
+                    q * 2, 0, c.img);
         if (++st == Cfg::A_STAGES) { st = 0; ph ^= 1u; }
       }
     }
@@ -317,9 +331,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
     const long long t_start = clock64();
     for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       for (int q = 0; q < chunks; ++q) {
-        mbar_wait_t(&a_ready[sa], pha, timed, w_a);
+        mbar_wait_t(&a_full[sa], pha, timed, w_a);
         tc_fence_after();
-        const uint32_t a_hi = a_desc_lo0 + a_base0 + (uint32_t)sa * (Cfg::A_STAGE_BYTES >> 4) + (uint32_t)(Cfg::A_RAW_BYTES >> 4);
+        const uint32_t a_hi = a_desc_lo0 + a_base0 + (uint32_t)sa * (Cfg::A_STAGE_BYTES >> 4);
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
           const int ky = tap / 3, kx = tap - 3 * ky;
@@ -339,7 +353,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
             if (elect_one()) {
               const uint32_t d = tmem_u + (uint32_t)((buf * MT + mt) * 2 * NT);
               const uint32_t da_hi = a_tap + mt_off[mt];
-              const uint32_t da_lo = da_hi + (uint32_t)(Cfg::A_HALF_BYTES >> 4);
+              const uint32_t da_lo = da_hi + 2u * (uint32_t)halo_px;              // lo planes follow the two hi planes
               umma_f16_w(d, da_hi, a_desc_hi, b_blk, b_desc_hi, IDESC_2N, first ? 0u : 1u);      // main | a_hi*w_lo
               umma_f16_w(d + NT, da_lo, a_desc_hi, b_blk, b_desc_hi, IDESC_1N, 1u);              // + a_lo*w_hi
               if (mt == MT - 1) {
@@ -358,74 +372,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
     }
     if (timed && lane == 0) {
       atomicAdd(p.stats + 0, (unsigned long long)(clock64() - t_start));   // MMA warp: total loop cycles
-      atomicAdd(p.stats + 1, (unsigned long long)w_a);                     //   waiting for split halo chunks
+      atomicAdd(p.stats + 1, (unsigned long long)w_a);                     //   waiting for TMA halo chunks
       atomicAdd(p.stats + 2, (unsigned long long)w_b);                     //   waiting for weight blocks
       atomicAdd(p.stats + 3, (unsigned long long)w_c);                     //   waiting for the epilogue to drain TMEM
-    }
-  } else if (warp >= 8 && warp < 12) {
-    // ================= hi/lo splitter (128 threads) =================
-    const int tid = threadIdx.x - 256;
-    int st = 0; uint32_t ph = 0;
-    const bool timed = p.stats != nullptr;
-    long long w_f = 0;
-    const long long t_start = clock64();
-    for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
-      for (int q = 0; q < chunks; ++q) {
-        mbar_wait_t<100>(&a_full[st], ph, timed, w_f);
-        const float4* raw = reinterpret_cast<const float4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES);
-        uint4* hi = reinterpret_cast<uint4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES + Cfg::A_RAW_BYTES);
-        uint4* lo = reinterpret_cast<uint4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES + Cfg::A_RAW_BYTES + Cfg::A_HALF_BYTES);
-        // item = (k-group kg of 8 channels, pixel): two fp32 planes (4+4 channels) -> one fp16 hi pixel + one fp16 lo pixel
-        const int n_items = 2 * halo_px;
-        for (int i0 = tid; i0 < n_items; i0 += 2 * 128) {
-          float4 va[2], vb[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int i = i0 + u * 128;
-            if (i < n_items) {
-              const int kg = (i >= halo_px) ? 1 : 0, px = i - kg * halo_px;
-              va[u] = raw[(2 * kg) * halo_px + px];
-              vb[u] = raw[(2 * kg + 1) * halo_px + px];
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int i = i0 + u * 128;
-            if (i < n_items) {
-              const float f[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
-              uint32_t h[4], l[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float x0 = fminf(f[2 * e], 65504.f), x1 = fminf(f[2 * e + 1], 65504.f);   // post-ReLU inputs: >= 0
-                const __half2 hh = __floats2half2_rn(x0, x1);
-                const float2 hf = __half22float2(hh);
-                const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-                h[e] = *reinterpret_cast<const uint32_t*>(&hh);
-                l[e] = *reinterpret_cast<const uint32_t*>(&ll);
-              }
-              hi[i] = make_uint4(h[0], h[1], h[2], h[3]);
-              lo[i] = make_uint4(l[0], l[1], l[2], l[3]);
-            }
-          }
-        }
-        fence_proxy_async();               // generic-proxy writes -> visible to the tensor-core (async) proxy
-        mbar_arrive(&a_ready[st]);
-        if (++st == Cfg::A_STAGES) { st = 0; ph ^= 1u; }
-      }
-    }
-    if (timed && tid == 0) {
-      atomicAdd(p.stats + 4, (unsigned long long)(clock64() - t_start));   // splitter: total loop cycles
-      atomicAdd(p.stats + 5, (unsigned long long)w_f);                     //   waiting for TMA halo chunks
     }
   } else if (warp >= 4) {
     // ================= epilogue (2 groups x 128 threads; warp w reads TMEM lanes 32*(w%4) ..) =================
     constexpr int CW = 16;                 // accumulator columns (channels) per step
-    const int grp = (warp >= 12) ? 1 : 0;  // group 0 drains even m-tiles, group 1 odd ones
+    const int grp = (warp >= 8) ? 1 : 0;   // group 0 drains even m-tiles, group 1 odd ones
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;          // accumulator row = pixel index inside the 16x8 m-tile
     const int prow = m >> 3, pcol = m & 7;
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-    const int cg_out = p.cout_total >> 2;
+    const int c8_out = p.cout_total >> 3;   // output k-groups (8 channels each) per hi or lo half
     uint32_t phc = 0;
     int buf = 0;
     const bool timed = p.stats != nullptr;
@@ -474,26 +433,32 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
             }
             const int hp = p.hout >> 1, wp = p.wout >> 1;
             if (((lane & 9) == 0) && (oy >> 1) < hp && (ox >> 1) < wp) {
-              float4* o = reinterpret_cast<float4*>(p.out) + (((size_t)c.img * cg_out + (ch0 >> 2)) * hp + (oy >> 1)) * wp + (ox >> 1);
-#pragma unroll
-              for (int k = 0; k < CW / 4; ++k) o[(size_t)k * hp * wp] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+              const size_t plane_o = (size_t)hp * wp;
+              uint4* o = reinterpret_cast<uint4*>(p.out) + ((size_t)c.img * 2 * c8_out + (ch0 >> 3)) * plane_o + (size_t)(oy >> 1) * wp + (ox >> 1);
+              store_h2_16(o, (size_t)c8_out * plane_o, plane_o, v);
             }
           } else if (p.ups) {
             if (inb) {
               const int hu = p.hout * 2, wu = p.wout * 2;
-              float4* o = reinterpret_cast<float4*>(p.out) + (((size_t)c.img * cg_out + (ch0 >> 2)) * hu + 2 * oy) * wu + 2 * ox;
+              const size_t plane_o = (size_t)hu * wu;
+              uint4* o = reinterpret_cast<uint4*>(p.out) + ((size_t)c.img * 2 * c8_out + (ch0 >> 3)) * plane_o + (size_t)(2 * oy) * wu + 2 * ox;
+              const size_t lo_off = (size_t)c8_out * plane_o;
 #pragma unroll
-              for (int k = 0; k < CW / 4; ++k) {
-                const float4 x = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                float4* ok = o + (size_t)k * hu * wu;
-                ok[0] = x; ok[1] = x; ok[wu] = x; ok[wu + 1] = x;
+              for (int k = 0; k < 2; ++k) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_h2(v[8 * k + 2 * e], v[8 * k + 2 * e + 1], h[e], l[e]);
+                const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]), lv = make_uint4(l[0], l[1], l[2], l[3]);
+                uint4* ok = o + (size_t)k * plane_o;
+                ok[0] = hv; ok[1] = hv; ok[wu] = hv; ok[wu + 1] = hv;
+                ok[lo_off] = lv; ok[lo_off + 1] = lv; ok[lo_off + wu] = lv; ok[lo_off + wu + 1] = lv;
               }
             }
           } else {
             if (inb) {
-              float4* o = reinterpret_cast<float4*>(p.out) + (((size_t)c.img * cg_out + (ch0 >> 2)) * p.hout + oy) * p.wout + ox;
-#pragma unroll
-              for (int k = 0; k < CW / 4; ++k) o[(size_t)k * p.hout * p.wout] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+              const size_t plane_o = (size_t)p.hout * p.wout;
+              uint4* o = reinterpret_cast<uint4*>(p.out) + ((size_t)c.img * 2 * c8_out + (ch0 >> 3)) * plane_o + (size_t)oy * p.wout + ox;
+              store_h2_16(o, (size_t)c8_out * plane_o, plane_o, v);
             }
           }
         }
@@ -518,7 +483,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
       }
       if (++buf == NBUF) { buf = 0; phc ^= 1u; }
     }
-    if (timed && (threadIdx.x == 128 || threadIdx.x == 384)) {
+    if (timed && (threadIdx.x == 128 || threadIdx.x == 256)) {
       atomicAdd(p.stats + 6, (unsigned long long)(clock64() - t_start) / 2);   // epilogue: total loop cycles (avg of 2 groups)
       atomicAdd(p.stats + 7, (unsigned long long)w_e / 2);                     //   waiting for MMAs
     }
@@ -537,13 +502,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
 
 // m-tile arrangement (TR x TC tiles of 16 rows x 8 cols) per CTA tile; also sizes the TMA box (engine.cu)
 void tc_tile_arrangement(int nt, int hout, int wout, int* tr, int* tc) {
-  if (nt == 64 && DCU_TC_MT64 == 4) {
-    if (wout >= 32) { *tr = 1; *tc = 4; }
-    else if (hout > 16 && wout > 8) { *tr = 2; *tc = 2; }
-    else { *tr = 1; *tc = 4; }
-    return;
-  }
-  // MT = 2
+  (void)nt;                      // MT = 2 for both NT: 16 rows x 16 cols (1x2) or 32 rows x 8 cols (2x1)
   if (wout % 16 == 0 || wout > 40) { *tr = 1; *tc = 2; }
   else if (hout > 16) { *tr = 2; *tc = 1; }
   else { *tr = 1; *tc = 2; }

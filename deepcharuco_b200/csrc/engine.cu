@@ -277,14 +277,14 @@ int build_3x3(Layer3x3& l, std::vector<const DcuConvLayer*> parts, int pad, int 
 static int make_tmap(CUtensorMap* tm, const float* base, int n, int cin, int h, int w, int box_w, int box_h) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  // [n][cin/4][h][w][4 floats] viewed as a 4-D tensor whose innermost dimension is a whole image row of 16-byte pixels
-  // (w*4 floats): the box row is then halo_w*16 contiguous bytes instead of 16, which is what the TMA engine moves
-  // efficiently; the shared-memory image is the same (planes of halo_h x halo_w 16-byte pixels).
-  cuuint64_t dims[4] = {(cuuint64_t)w * 4, (cuuint64_t)h, (cuuint64_t)(cin / 4), (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)w * 16, (cuuint64_t)w * h * 16, (cuuint64_t)w * h * 16 * (cin / 4)};
-  cuuint32_t box[4] = {(cuuint32_t)box_w * 4, (cuuint32_t)box_h, 4, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+  // H2 activations: __half [n][hi|lo][cin/8][h][w][8].  Innermost dimension = a whole image row of 16-byte pixels (w*8
+  // halves) so the box row is halo_w*16 contiguous bytes; box = {8*halo_w, halo_h, 2 k-groups (16 channels), hi|lo, 1}.
+  cuuint64_t dims[5] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)(cin / 8), 2, (cuuint64_t)n};
+  const cuuint64_t plane = (cuuint64_t)w * h * 16;
+  cuuint64_t strides[4] = {(cuuint64_t)w * 16, plane, plane * (cin / 8), plane * (cin / 8) * 2};
+  cuuint32_t box[5] = {(cuuint32_t)box_w * 8, (cuuint32_t)box_h, 2, 2, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
@@ -323,8 +323,9 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
 }
 
 static int run_first(DcuEngine* e, const FirstLayer& f, const uint8_t* in_u8, const float* in_f32, float* out, int n,
-                     int hin, int win, cudaStream_t s) {
+                     int hin, int win, int out_h2, cudaStream_t s) {
   FirstConvParams p{};
+  p.out_h2 = out_h2;
   p.in_u8 = in_u8; p.in_f32 = in_f32; p.lut = e->lut.as<float>(); p.out = out; p.w = f.w.as<float>();
   p.bias = f.bias.as<float>(); p.alpha = f.alpha.as<float>(); p.beta = f.beta.as<float>();
   p.n = n; p.hin = hin; p.win = win; p.pad = f.pad; p.hout = hin + 2 * f.pad - 2; p.wout = win + 2 * f.pad - 2;
@@ -349,7 +350,8 @@ static int detector_group(DcuEngine* e, const uint8_t* frames, const float* imag
   for (int f0 = 0; f0 < n; f0 += e->mb1) {
     const int m = std::min(e->mb1, n - f0);
     if ((rc = run_first(e, e->det_first, frames ? frames + (size_t)f0 * H * W : nullptr,
-                        images ? images + (size_t)f0 * H * W : nullptr, a0, m, H, W, s))) return rc;          // conv1a
+                        images ? images + (size_t)f0 * H * W : nullptr, a0, m, H, W, e->conv_impl == DCU_CONV_TCGEN05, s)))
+      return rc;                                                                                                // conv1a
     if ((rc = run_3x3(e, e->det[0], e->conv_impl, a0, a1, m, H, W, nullptr, s))) return rc;                     // conv1b + pool
     if ((rc = run_3x3(e, e->det[1], e->conv_impl, a1, a0, m, H / 2, W / 2, nullptr, s))) return rc;             // conv2a
     if ((rc = run_3x3(e, e->det[2], e->conv_impl, a0, s2 + f0 * s2_frame, m, H / 2, W / 2, nullptr, s))) return rc;  // conv2b + pool
@@ -363,6 +365,7 @@ static int detector_group(DcuEngine* e, const uint8_t* frames, const float* imag
   hp.in = e->heads.as<float>(); hp.w_loc = e->w_loc.as<float>(); hp.b_loc = e->b_loc.as<float>();
   hp.w_ids = e->w_ids.as<float>(); hp.b_ids = e->b_ids.as<float>(); hp.loc = loc; hp.ids = ids;
   hp.n = n; hp.h = H / 8; hp.w = W / 8; hp.n_ids1 = e->cfg.n_ids + 1;
+  hp.in_h2 = e->conv_impl == DCU_CONV_TCGEN05;
   e->prof_begin(2, 2.0 * 256.0 * (65 + hp.n_ids1) * (double)hp.h * hp.w * n, s);
   launch_heads_1x1(hp, s);                                                                                       // convPb, convDb
   e->prof_end(s);
@@ -399,7 +402,8 @@ static int refine_run(DcuEngine* e, const float* patches, const int32_t* xy, int
     const int m = std::min(e->rp, p - p0);
     unsigned long long* keys = e->keys.as<unsigned long long>() + p0;
     CK(cudaMemsetAsync(keys, 0, (size_t)m * sizeof(unsigned long long), s));
-    if ((rc = run_first(e, e->ref_first, nullptr, patches + (size_t)p0 * 576, a0, m, 24, 24, s))) return rc;   // conv1a -> 22
+    if ((rc = run_first(e, e->ref_first, nullptr, patches + (size_t)p0 * 576, a0, m, 24, 24, e->conv_impl == DCU_CONV_TCGEN05, s)))
+      return rc;                                                                                  // conv1a -> 22
     if ((rc = run_3x3(e, e->ref[0], e->conv_impl, a0, a1, m, 22, 22, nullptr, s))) return rc;   // conv1b -> 20
     if ((rc = run_3x3(e, e->ref[1], e->conv_impl, a1, a0, m, 20, 20, nullptr, s))) return rc;   // conv2a -> 18
     if ((rc = run_3x3(e, e->ref[2], e->conv_impl, a0, a1, m, 18, 18, nullptr, s))) return rc;   // conv2b -> 16 -> pool 8
@@ -780,14 +784,17 @@ int dcu_debug_conv_layer(DcuEngine* e, int net, int layer, int conv_impl, const 
   CK(tin.alloc((size_t)n * cin * h * w * 4));
   CK(tout.alloc((size_t)n * cout * hf * wf * 4));
   int rc = DCU_OK;
+  const bool h2 = !fl && conv_impl == DCU_CONV_TCGEN05;     // the tcgen05 kernel reads and writes the H2 layout
   if (fl) {
-    rc = run_first(e, *fl, nullptr, in_dev, tout.as<float>(), n, h, w, s);
+    rc = run_first(e, *fl, nullptr, in_dev, tout.as<float>(), n, h, w, 0, s);
   } else {
-    launch_nchw_to_c4(in_dev, tin.as<float>(), n, cin, h, w, s);
+    if (h2) launch_nchw_to_h2(in_dev, tin.p, n, cin, h, w, s);
+    else launch_nchw_to_c4(in_dev, tin.as<float>(), n, cin, h, w, s);
     rc = run_3x3(e, *l, conv_impl, tin.as<float>(), tout.as<float>(), n, h, w, nullptr, s);
   }
   if (rc == DCU_OK) {
-    launch_c4_to_nchw(tout.as<float>(), out_dev, n, cout, hf, wf, s);
+    if (h2) launch_h2_to_nchw(tout.p, out_dev, n, cout, hf, wf, s);
+    else launch_c4_to_nchw(tout.as<float>(), out_dev, n, cout, hf, wf, s);
     cudaError_t ce = cudaStreamSynchronize(s);
     if (ce != cudaSuccess) rc = fail(DCU_ERR_CUDA, std::string("dcu_debug_conv_layer: ") + cudaGetErrorString(ce));
   }
