@@ -334,37 +334,38 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
         mbar_wait_t(&a_full[sa], pha, timed, w_a);
         tc_fence_after();
         const uint32_t a_hi = a_desc_lo0 + a_base0 + (uint32_t)sa * (Cfg::A_STAGE_BYTES >> 4);
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          const int ky = tap / 3, kx = tap - 3 * ky;
-          if (kx == 0) {                         // TPB == 3: one weight stage per kernel row
-            mbar_wait_t(&b_full[sb], phb, timed, w_b);
-            tc_fence_after();
-          }
-          const uint32_t a_tap = a_hi + (uint32_t)(ky * g.halo_w + kx);
-          const uint32_t b_blk = b_desc_lo0 + b_base0 + (uint32_t)sb * (Cfg::B_STAGE_BYTES >> 4) + (uint32_t)kx * (Cfg::B_BLOCK_BYTES >> 4);
-          const bool first = (q | tap) == 0;
+        if (q == 0) {                            // first touch of this accumulator set in this tile: wait for the epilogue
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            if (first) {                       // first touch of this m-tile's columns in this tile: wait for the epilogue
-              mbar_wait_t(&acc_empty[buf * MT + mt], phc ^ 1u, timed, w_c);
-              tc_fence_after();
-            }
-            if (elect_one()) {
-              const uint32_t d = tmem_u + (uint32_t)((buf * MT + mt) * 2 * NT);
-              const uint32_t da_hi = a_tap + mt_off[mt];
-              const uint32_t da_lo = da_hi + 2u * (uint32_t)halo_px;              // lo planes follow the two hi planes
-              umma_f16_w(d, da_hi, a_desc_hi, b_blk, b_desc_hi, IDESC_2N, first ? 0u : 1u);      // main | a_hi*w_lo
-              umma_f16_w(d + NT, da_lo, a_desc_hi, b_blk, b_desc_hi, IDESC_1N, 1u);              // + a_lo*w_hi
-              if (mt == MT - 1) {
-                if (kx == 2) umma_commit(&b_empty[sb]);
-                if (tap == 8) umma_commit(&a_empty[sa]);
-                if (tap == 8 && q == chunks - 1) umma_commit(&acc_full[buf]);
+          for (int mt = 0; mt < MT; ++mt) mbar_wait_t(&acc_empty[buf * MT + mt], phc ^ 1u, timed, w_c);
+          tc_fence_after();
+        }
+#pragma unroll 1
+        for (int ky = 0; ky < 3; ++ky) {         // one weight stage (TPB = 3 taps) per kernel row
+          mbar_wait_t(&b_full[sb], phb, timed, w_b);
+          tc_fence_after();
+          const uint32_t a_row = a_hi + (uint32_t)(ky * g.halo_w);
+          const uint32_t b_row = b_desc_lo0 + b_base0 + (uint32_t)sb * (Cfg::B_STAGE_BYTES >> 4);
+          // ONE elected region per kernel row (3 taps x MT m-tiles x 2 MMAs): the elect / reconverge / syncwarp sequence
+          // costs ~100 cycles, which dominated when it wrapped every pair of MMAs (profiles/r1_tc_variants.txt)
+          if (elect_one()) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint32_t b_blk = b_row + (uint32_t)kx * (Cfg::B_BLOCK_BYTES >> 4);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t d = tmem_u + (uint32_t)((buf * MT + mt) * 2 * NT);
+                const uint32_t da_hi = a_row + (uint32_t)kx + mt_off[mt];
+                const uint32_t da_lo = da_hi + 2u * (uint32_t)halo_px;            // lo planes follow the two hi planes
+                umma_f16_w(d, da_hi, a_desc_hi, b_blk, b_desc_hi, IDESC_2N, (q | ky | kx) ? 1u : 0u);   // main | a_hi*w_lo
+                umma_f16_w(d + NT, da_lo, a_desc_hi, b_blk, b_desc_hi, IDESC_1N, 1u);                     // + a_lo*w_hi
               }
             }
-            __syncwarp();
+            umma_commit(&b_empty[sb]);
+            if (ky == 2) umma_commit(&a_empty[sa]);
+            if (ky == 2 && q == chunks - 1) umma_commit(&acc_full[buf]);
           }
-          if (kx == 2) { if (++sb == B_STAGES) { sb = 0; phb ^= 1u; } }
+          __syncwarp();
+          if (++sb == B_STAGES) { sb = 0; phb ^= 1u; }
         }
         if (++sa == Cfg::A_STAGES) { sa = 0; pha ^= 1u; }
       }
