@@ -33,6 +33,11 @@ struct ConvParams {
   float head_b;           // convPb bias
   unsigned long long* head_key;  // [n] packed (orderable heat value << 32 | ~index)
   float* heat;            // optional [n][hout][wout] dump of the heat map (tests), may be null
+  // tcgen05 path, 1x1 "logits" mode (detector heads convPb / convDb, net.py:74,77): ksize == 1, no BN / ReLU, fp32 NCHW out
+  int ksize;              // 3 (default when 0) or 1
+  int cin_offset;         // first input channel inside the input tensor (multiple of 8)
+  float* logits;          // [n][n_valid][hout][wout] fp32, or null
+  int n_valid;            // real output channels (the weight block is zero-padded to NT rows)
   float wscale_inv;       // tcgen05 path: 2^-s, undoes the power-of-two weight scaling of the fp16 split (1.0 otherwise)
   unsigned long long* stats;   // optional [8] cycle counters for the tcgen05 kernel's roles (profiling), may be null
 };

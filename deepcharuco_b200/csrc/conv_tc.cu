@@ -228,7 +228,7 @@ __device__ __forceinline__ TileCoord decode_tile(long long t, const TcGeo& g) {
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-template <int NT>
+template <int NT, int KS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, const float* __restrict__ w_blocks,
                   const TcGeo g) {
@@ -236,6 +236,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
   constexpr int MT = Cfg::MT;
   constexpr int NBUF = Cfg::NBUF;
   constexpr int B_STAGES = Cfg::B_STAGES;
+  constexpr int ROWS = KS, TPR = KS, TAPS = KS * KS;       // kernel rows, taps per row (= per weight stage), taps
   // NB: no integer round-trip on this pointer -- it would demote every shared-memory access below to a generic LD/ST
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* a_smem = smem_raw;
@@ -286,7 +287,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
         mbar_wait<200>(&a_empty[st], ph ^ 1u);
         mbar_expect_tx(&a_full[st], (uint32_t)halo_px * 64u);
         tma_load_5d(smem_u32(a_smem + (size_t)st * Cfg::A_STAGE_BYTES), &tmap, &a_full[st], (c.x0 - p.pad) * 8, c.y0 - p.pad,
-                    q * 2, 0, c.img);
+                    (p.cin_offset >> 3) + q * 2, 0, c.img);
         if (++st == Cfg::A_STAGES) { st = 0; ph ^= 1u; }
       }
     }
@@ -298,12 +299,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
       // every CTA streams the same weight blocks at about the same time: read them from one of g.w_copies replicas so the
       // requests spread over more L2 slices (and both dies) instead of hammering the few slices that home one copy
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(w_blocks) + (size_t)(blockIdx.x % g.w_copies) * g.w_copy_bytes +
-                            (size_t)c.slice * chunks * 9 * Cfg::B_BLOCK_BYTES;
-      for (int blk = 0; blk < chunks * 9; blk += Cfg::TPB) {
+                            (size_t)c.slice * chunks * TAPS * Cfg::B_BLOCK_BYTES;
+      for (int blk = 0; blk < chunks * TAPS; blk += TPR) {
         mbar_wait<200>(&b_empty[st], ph ^ 1u);
-        mbar_expect_tx(&b_full[st], (uint32_t)Cfg::B_STAGE_BYTES);
+        mbar_expect_tx(&b_full[st], (uint32_t)(TPR * Cfg::B_BLOCK_BYTES));
         bulk_load(smem_u32(b_smem + (size_t)st * Cfg::B_STAGE_BYTES), wsrc + (size_t)blk * Cfg::B_BLOCK_BYTES,
-                  (uint32_t)Cfg::B_STAGE_BYTES, &b_full[st]);
+                  (uint32_t)(TPR * Cfg::B_BLOCK_BYTES), &b_full[st]);
         if (++st == B_STAGES) { st = 0; ph ^= 1u; }
       }
     }
@@ -340,7 +341,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
           tc_fence_after();
         }
 #pragma unroll 1
-        for (int ky = 0; ky < 3; ++ky) {         // one weight stage (TPB = 3 taps) per kernel row
+        for (int ky = 0; ky < ROWS; ++ky) {      // one weight stage (TPR taps) per kernel row
           mbar_wait_t(&b_full[sb], phb, timed, w_b);
           tc_fence_after();
           const uint32_t a_row = a_hi + (uint32_t)(ky * g.halo_w);
@@ -349,7 +350,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
           // costs ~100 cycles, which dominated when it wrapped every pair of MMAs (profiles/r1_tc_variants.txt)
           if (elect_one()) {
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
+            for (int kx = 0; kx < TPR; ++kx) {
               const uint32_t b_blk = b_row + (uint32_t)kx * (Cfg::B_BLOCK_BYTES >> 4);
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
@@ -361,8 +362,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
               }
             }
             umma_commit(&b_empty[sb]);
-            if (ky == 2) umma_commit(&a_empty[sa]);
-            if (ky == 2 && q == chunks - 1) umma_commit(&acc_full[buf]);
+            if (ky == ROWS - 1) umma_commit(&a_empty[sa]);
+            if (ky == ROWS - 1 && q == chunks - 1) umma_commit(&acc_full[buf]);
           }
           __syncwarp();
           if (++sb == B_STAGES) { sb = 0; phb ^= 1u; }
@@ -413,6 +414,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
             for (int j = 0; j < CW; ++j) v[j] = (v[j] + sm[j]) * p.wscale_inv;   // main + (a_hi*w_lo + a_lo*w_hi), undo 2^s
           }
           const int ch0 = ch_base + cc * CW;
+          if (p.logits != nullptr) {
+            // detector heads: logits = acc + bias, no activation, fp32 NCHW (the layout pred_argmax reads, model_utils.py:72)
+            if (inb) {
+              const size_t plane_o = (size_t)p.hout * p.wout;
+              float* o = p.logits + (size_t)c.img * p.n_valid * plane_o + (size_t)oy * p.wout + ox;
+#pragma unroll
+              for (int j = 0; j < CW; ++j)
+                if (ch0 + j < p.n_valid) o[(size_t)(ch0 + j) * plane_o] = v[j] + prm[ch0 + j];
+            }
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < CW; j += 4) {
             const float4 bi = *reinterpret_cast<const float4*>(&prm[ch0 + j]);
@@ -510,19 +522,19 @@ void tc_tile_arrangement(int nt, int hout, int wout, int* tr, int* tc) {
 }
 
 int tc_supported_shape(int cin, int cout) {
-  if (cin % 16 != 0 || cin > 128) return 0;
+  if (cin % 16 != 0 || cin > 256) return 0;
   if (cout == 64) return 64;
   if (cout % 128 == 0 && cout <= 512) return 128;
   return 0;
 }
 
-template <int NT>
+template <int NT, int KS>
 static cudaError_t launch_nt(const ConvParams& p, const float* w_blocks, int n_slices, int w_copies, const CUtensorMap* tm,
                              int sm_count, cudaStream_t s) {
   using Cfg = TcCfg<NT>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<NT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
@@ -534,20 +546,25 @@ static cudaError_t launch_nt(const ConvParams& p, const float* w_blocks, int n_s
   g.tiles_x = ceil_div(p.wout, 8 * g.tc); g.tiles_y = ceil_div(p.hout, 16 * g.tr);
   g.slices = n_slices;
   g.w_copies = w_copies < 1 ? 1 : w_copies;
-  g.w_copy_bytes = (long long)n_slices * (p.cin / 16) * 9 * Cfg::B_BLOCK_BYTES;
+  g.w_copy_bytes = (long long)n_slices * (p.cin / 16) * (KS * KS) * Cfg::B_BLOCK_BYTES;
   g.total_tiles = (long long)p.n * g.slices * g.tiles_x * g.tiles_y;
   if (g.total_tiles <= 0) return cudaSuccess;
   const int grid = (int)(g.total_tiles < sm_count ? g.total_tiles : sm_count);
-  conv3x3_tc_kernel<NT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(*tm, p, w_blocks, g);
+  conv3x3_tc_kernel<NT, KS><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(*tm, p, w_blocks, g);
   return cudaGetLastError();
 }
 
 cudaError_t launch_conv3x3_tc(const ConvParams& p, const float* w_blocks, int n_slices, int w_copies, const void* tmap_in,
                               int sm_count, cudaStream_t s) {
   const CUtensorMap* tm = reinterpret_cast<const CUtensorMap*>(tmap_in);
-  const int nt = tc_supported_shape(p.cin, p.cout_total);
-  if (nt == 64) return launch_nt<64>(p, w_blocks, n_slices, w_copies, tm, sm_count, s);
-  if (nt == 128) return launch_nt<128>(p, w_blocks, n_slices, w_copies, tm, sm_count, s);
+  const int nt = p.cout_total / n_slices;        // output channels per CTA pass (weight block rows)
+  if (p.ksize == 1) {
+    if (nt == 64) return launch_nt<64, 1>(p, w_blocks, n_slices, w_copies, tm, sm_count, s);
+    if (nt == 128) return launch_nt<128, 1>(p, w_blocks, n_slices, w_copies, tm, sm_count, s);
+    return cudaErrorInvalidValue;
+  }
+  if (nt == 64) return launch_nt<64, 3>(p, w_blocks, n_slices, w_copies, tm, sm_count, s);
+  if (nt == 128) return launch_nt<128, 3>(p, w_blocks, n_slices, w_copies, tm, sm_count, s);
   return cudaErrorInvalidValue;
 }
 

@@ -92,35 +92,38 @@ cudaError_t upload(DevBuf& b, const std::vector<float>& h) {
 // channels), tap t:   block[(s*chunks + q)*9 + t] = [2 k-groups of 8 channels][2*NT rows: NT hi rows then NT lo rows][8 fp16]
 // so that [w_hi | w_lo] is ONE K-major operand with N' = 2*NT.  Weights are pre-multiplied by `scale` (a power of two,
 // exact) so that w_lo = fp16(w*scale - w_hi) stays in fp16's normal range; the kernel's epilogue multiplies by 1/scale.
-float tc_weight_scale(const std::vector<const float*>& ws, const std::vector<int>& couts, int cin) {
+float tc_weight_scale(const std::vector<const float*>& ws, const std::vector<int>& couts, int cin, int taps = 9) {
   float mx = 0.f;
   for (size_t t = 0; t < ws.size(); ++t)
-    for (size_t i = 0; i < (size_t)couts[t] * cin * 9; ++i) mx = std::max(mx, std::fabs(ws[t][i]));
+    for (size_t i = 0; i < (size_t)couts[t] * cin * taps; ++i) mx = std::max(mx, std::fabs(ws[t][i]));
   if (!(mx > 0.f)) return 1.f;
   return std::exp2(std::floor(std::log2(32768.0f / mx)));      // |w*scale| < 65504 with a 2x margin
 }
 
-std::vector<uint16_t> pack_tc(const std::vector<const float*>& ws, const std::vector<int>& couts, int cin, int nt, float scale) {
+std::vector<uint16_t> pack_tc(const std::vector<const float*>& ws, const std::vector<int>& couts, int cin, int nt, float scale,
+                              int taps = 9, int pad_rows_to = 0) {
   int cout_total = 0;
   for (int c : couts) cout_total += c;
-  const int slices = cout_total / nt, chunks = cin / 16;
+  const int rows_total = std::max(cout_total, pad_rows_to);     // rows beyond cout_total are zero (1x1 heads padded to NT)
+  const int slices = rows_total / nt, chunks = cin / 16;
   const size_t blk = (size_t)2 * (2 * nt) * 8;      // halves per block
-  std::vector<uint16_t> out((size_t)slices * chunks * 9 * blk);
-  std::vector<const float*> row(cout_total);
+  std::vector<uint16_t> out((size_t)slices * chunks * taps * blk, 0);
+  std::vector<const float*> row(rows_total, nullptr);
   {
     int o = 0;
     for (size_t t = 0; t < ws.size(); ++t)
-      for (int k = 0; k < couts[t]; ++k) row[o++] = ws[t] + (size_t)k * cin * 9;
+      for (int k = 0; k < couts[t]; ++k) row[o++] = ws[t] + (size_t)k * cin * taps;
   }
   for (int s = 0; s < slices; ++s)
     for (int q = 0; q < chunks; ++q)
-      for (int tap = 0; tap < 9; ++tap) {
-        uint16_t* b = out.data() + (((size_t)s * chunks + q) * 9 + tap) * blk;
+      for (int tap = 0; tap < taps; ++tap) {
+        uint16_t* b = out.data() + (((size_t)s * chunks + q) * taps + tap) * blk;
         for (int kg = 0; kg < 2; ++kg)
           for (int n = 0; n < nt; ++n)
             for (int e = 0; e < 8; ++e) {
               const int ci = q * 16 + kg * 8 + e;
-              const float w = row[s * nt + n][(size_t)ci * 9 + tap] * scale;
+              if (row[s * nt + n] == nullptr) continue;
+              const float w = row[s * nt + n][(size_t)ci * taps + tap] * scale;
               const __half hi = __float2half_rn(w);
               const __half lo = __float2half_rn(w - __half2float(hi));
               uint16_t hb, lb;
@@ -168,6 +171,8 @@ struct DcuEngine {
   FirstLayer det_first;
   Layer3x3 det[8];              // 1b,2a,2b,3a,3b,4a,4b,(Pa|Da)
   DevBuf w_loc, b_loc, w_ids, b_ids;
+  // the same 1x1 heads for the tcgen05 kernel: weight blocks padded to NT rows, padded bias, dummy BN vectors
+  struct TcHead { DevBuf w, bias, ones; float scale = 1.f; int nt = 0, copies = 1; } tc_loc, tc_ids;
   // refinenet
   FirstLayer ref_first;
   Layer3x3 ref[10];             // 1b,2a,2b,3a,3b,4a,4b,5a,5b,Pa
@@ -205,7 +210,7 @@ struct DcuEngine {
   int32_t* h_kpts = nullptr; float* h_refined = nullptr; int32_t* h_total = nullptr;
 
   ~DcuEngine() {
-    DevBuf* all[] = {&w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
+    DevBuf* all[] = {&tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
                      &ids, &counts, &offsets, &total, &kpts, &patches, &keys, &refined, &scan_state, &frames};
     for (DevBuf* b : all) b->release();
     FirstLayer* fl[] = {&det_first, &ref_first};
@@ -274,7 +279,7 @@ int build_3x3(Layer3x3& l, std::vector<const DcuConvLayer*> parts, int pad, int 
 // ---------------------------------------------------------------------------------------------------
 // layer runners
 // ---------------------------------------------------------------------------------------------------
-static int make_tmap(CUtensorMap* tm, const float* base, int n, int cin, int h, int w, int box_w, int box_h) {
+static int make_tmap(CUtensorMap* tm, const void* base, int n, int cin, int h, int w, int box_w, int box_h) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   // H2 activations: __half [n][hi|lo][cin/8][h][w][8].  Innermost dimension = a whole image row of 16-byte pixels (w*8
@@ -284,7 +289,7 @@ static int make_tmap(CUtensorMap* tm, const float* base, int n, int cin, int h, 
   cuuint64_t strides[4] = {(cuuint64_t)w * 16, plane, plane * (cin / 8), plane * (cin / 8) * 2};
   cuuint32_t box[5] = {(cuuint32_t)box_w * 8, (cuuint32_t)box_h, 2, 2, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<float*>(base), dims, strides, box, estr,
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
@@ -303,6 +308,7 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
   if (hf) { p.head_w = hf->w; p.head_b = hf->b; p.head_key = hf->keys; p.heat = hf->heat; }
   p.stats = g_tc_stats;
   p.wscale_inv = (impl == DCU_CONV_TCGEN05) ? 1.0f / l.tc_scale : 1.0f;
+  p.ksize = 3;
   if (n <= 0) return DCU_OK;
   e->prof_begin(0, 2.0 * 9.0 * l.cin * l.cout * (double)p.hout * p.wout * n, s);
   if (impl == DCU_CONV_TCGEN05) {
@@ -361,11 +367,33 @@ static int detector_group(DcuEngine* e, const uint8_t* frames, const float* imag
   if ((rc = run_3x3(e, e->det[5], e->conv_impl, a1, a0, n, H / 8, W / 8, nullptr, s))) return rc;               // conv4a
   if ((rc = run_3x3(e, e->det[6], e->conv_impl, a0, a1, n, H / 8, W / 8, nullptr, s))) return rc;               // conv4b
   if ((rc = run_3x3(e, e->det[7], e->conv_impl, a1, e->heads.as<float>(), n, H / 8, W / 8, nullptr, s))) return rc;  // convPa | convDa
+  if (e->conv_impl == DCU_CONV_TCGEN05) {
+    // convPb / convDb on the tensor cores: 1x1 "logits" mode of the same kernel, reading cPa / cDa from the H2 tensor
+    for (int which = 0; which < 2; ++which) {
+      const DcuEngine::TcHead& hd = which ? e->tc_ids : e->tc_loc;
+      ConvParams p{};
+      p.in = e->heads.as<float>(); p.bias = hd.bias.as<float>(); p.alpha = hd.ones.as<float>(); p.beta = hd.ones.as<float>();
+      p.n = n; p.cin = 256; p.cout_total = hd.nt; p.hin = H / 8; p.win = W / 8; p.hout = H / 8; p.wout = W / 8;
+      p.ksize = 1; p.cin_offset = which ? 256 : 0; p.logits = which ? ids : loc; p.n_valid = which ? e->cfg.n_ids + 1 : 65;
+      p.wscale_inv = 1.0f / hd.scale; p.stats = nullptr;
+      int tr, tc;
+      tc_tile_arrangement(hd.nt, p.hout, p.wout, &tr, &tc);
+      CUtensorMap tm;
+      if ((rc = make_tmap(&tm, e->heads.p, n, 512, H / 8, W / 8, 8 * tc + 2, 16 * tr + 2))) return rc;
+      e->prof_begin(2, 2.0 * 256.0 * p.n_valid * (double)p.hout * p.wout * n, s);
+      cudaError_t ce = launch_conv3x3_tc(p, hd.w.as<float>(), 1, hd.copies, &tm, e->sm_count, s);
+      e->prof_end(s);
+      if (ce != cudaSuccess) return fail(DCU_ERR_CUDA, std::string("tcgen05 1x1 head launch: ") + cudaGetErrorString(ce));
+      e->launches++;
+    }
+    CK(cudaGetLastError());
+    return DCU_OK;
+  }
   HeadParams hp{};
   hp.in = e->heads.as<float>(); hp.w_loc = e->w_loc.as<float>(); hp.b_loc = e->b_loc.as<float>();
   hp.w_ids = e->w_ids.as<float>(); hp.b_ids = e->b_ids.as<float>(); hp.loc = loc; hp.ids = ids;
   hp.n = n; hp.h = H / 8; hp.w = W / 8; hp.n_ids1 = e->cfg.n_ids + 1;
-  hp.in_h2 = e->conv_impl == DCU_CONV_TCGEN05;
+  hp.in_h2 = 0;
   e->prof_begin(2, 2.0 * 256.0 * (65 + hp.n_ids1) * (double)hp.h * hp.w * n, s);
   launch_heads_1x1(hp, s);                                                                                       // convPb, convDb
   e->prof_end(s);
@@ -468,6 +496,24 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   TRYC(upload(e->b_loc, std::vector<float>(D[9].bias, D[9].bias + 65)));
   TRYC(upload(e->w_ids, std::vector<float>(D[11].weight, D[11].weight + (size_t)(cfg->n_ids + 1) * 256)));
   TRYC(upload(e->b_ids, std::vector<float>(D[11].bias, D[11].bias + cfg->n_ids + 1)));
+  {
+    auto build_head = [&](DcuEngine::TcHead& h, const DcuConvLayer& L, int nt) -> cudaError_t {
+      h.nt = nt;
+      h.scale = tc_weight_scale({L.weight}, {L.cout}, 256, 1);
+      const std::vector<uint16_t> blocks = pack_tc({L.weight}, {L.cout}, 256, nt, h.scale, 1, nt);
+      h.copies = 4;
+      cudaError_t ce = h.w.alloc(blocks.size() * 2 * h.copies);
+      for (int c = 0; c < h.copies && ce == cudaSuccess; ++c)
+        ce = cudaMemcpy(h.w.as<uint8_t>() + (size_t)c * blocks.size() * 2, blocks.data(), blocks.size() * 2, cudaMemcpyHostToDevice);
+      if (ce != cudaSuccess) return ce;
+      std::vector<float> b(nt, 0.f), ones(nt, 1.f);
+      std::copy(L.bias, L.bias + L.cout, b.begin());
+      if ((ce = upload(h.bias, b)) != cudaSuccess) return ce;
+      return upload(h.ones, ones);
+    };
+    TRYC(build_head(e->tc_loc, D[9], 128));
+    TRYC(build_head(e->tc_ids, D[11], cfg->n_ids + 1 <= 64 ? 64 : 128));
+  }
   // refinenet: conv1a,1b,2a,2b,3a,3b,4a,4b,5a,5b,Pa,Pb  (refinenet.py:22-47)
   e->has_ref = (R != nullptr && n_ref == 12);
   if (R != nullptr && n_ref != 0 && n_ref != 12) { delete e; return fail(DCU_ERR_INVALID, "dcu_create: need 12 RefineNet layers"); }
