@@ -248,6 +248,14 @@ def main():
     step_ms_prof = conv_ms + dec_ms + first_ms + heads_ms
     dec_bytes += 2 * (total_k * (2304 + 2304 + 16))          # + K*(patch read + patch write + record), 2 profiled steps
 
+    # DRAM traffic of the dominant kernel: from the committed ncu capture of this same workload (per-launch average)
+    conv_traffic, traffic_src = None, None
+    try:
+        ls = json.load(open(os.path.join(ROOT, "profiles", "r1_launch_summary.json")))
+        conv_traffic = ls["conv3x3_tc"]["dram_bytes_per_launch"]
+        traffic_src = "profiles/r1_launch_summary.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, average per launch)"
+    except Exception:
+        pass
     if rank == 0:
         impl_name = {Nn.CONV_FFMA: "ffma-fp32", Nn.CONV_TCGEN05: "tcgen05-f16-hi/lo-split(3 products, fp32 accumulate)"}[eng.conv_impl]
         line = dict(
@@ -263,10 +271,14 @@ def main():
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      ms_per_step=ms_e2e / args.steps, api="dcu_infer_batch_host (pinned host u8 frames in, packed keypoints out)"),
             gpu_launches=int(launches),
-            roofline=dict(bound="tensor", kernel="conv3x3 (all 17 layer shapes, aggregated over launches)",
+            roofline=dict(bound="tensor", kernel="conv3x3_tc_kernel (all 3x3 layer shapes of both networks, aggregated over launches)",
                           achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf if peak_tf else None,
                           peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
-                          traffic=None, launches=int(conv_n), kernel_ms_per_step=conv_ms / 2,
+                          note="achieved = ALGORITHMIC flops (2*MAC of the fp32 convolutions, SURVEY.md 8d).  The parity-safe fp16 hi/lo "
+                               "split issues 3 tensor-core products per MAC, so the tensor pipes run at issued = 3 x achieved.",
+                          issued_tflops=3.0 * achieved_tf if eng.conv_impl == Nn.CONV_TCGEN05 else None,
+                          issued_frac=(3.0 * achieved_tf / peak_tf) if (peak_tf and eng.conv_impl == Nn.CONV_TCGEN05) else None,
+                          traffic=conv_traffic, traffic_source=traffic_src, launches=int(conv_n), kernel_ms_per_step=conv_ms / 2,
                           share_of_step=conv_ms / step_ms_prof if step_ms_prof else None,
                           decode_gather=dict(bound="hbm", achieved=(dec_bytes / (dec_ms / 1e3) / 1e9) if dec_ms > 0 else 0.0,
                                              peak=peaks["hbm"], unit="GB/s", launches=int(dec_n), kernel_ms_per_step=dec_ms / 2)),
