@@ -181,6 +181,11 @@ struct DcuEngine {
   DevBuf lut;                   // [256] (x-128)/255
   int mb1 = 32, mb2 = 256, rp = 1024;   // micro-batch sizes: full-res layers, low-res layers, RefineNet patches
   DevBuf act[2];                // ping-pong activation buffers
+  DevBuf c1[2];                 // conv1a outputs, double-buffered: conv1a of micro-batch i+1 (HBM-write bound, side stream)
+                                // overlaps conv1b/2a/2b of micro-batch i (tensor bound, caller's stream)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  bool overlap_first = true;
   DevBuf stage2_in;             // conv2b output for mb2 frames (input of conv3a)
   DevBuf heads;                 // (Pa|Da) output for mb2 frames
   DevBuf loc, ids;              // [mb2] logits when the caller does not want them
@@ -210,7 +215,10 @@ struct DcuEngine {
   int32_t* h_kpts = nullptr; float* h_refined = nullptr; int32_t* h_total = nullptr;
 
   ~DcuEngine() {
-    DevBuf* all[] = {&tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
+    if (side) cudaStreamDestroy(side);
+    if (ev_start) cudaEventDestroy(ev_start);
+    for (int i = 0; i < 2; ++i) { if (ev_done[i]) cudaEventDestroy(ev_done[i]); if (ev_free[i]) cudaEventDestroy(ev_free[i]); }
+    DevBuf* all[] = {&c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
                      &ids, &counts, &offsets, &total, &kpts, &patches, &keys, &refined, &scan_state, &frames};
     for (DevBuf* b : all) b->release();
     FirstLayer* fl[] = {&det_first, &ref_first};
@@ -353,12 +361,37 @@ static int detector_group(DcuEngine* e, const uint8_t* frames, const float* imag
   float* s2 = e->stage2_in.as<float>();
   const size_t s2_frame = (size_t)64 * (H / 4) * (W / 4);
   int rc;
-  for (int f0 = 0; f0 < n; f0 += e->mb1) {
-    const int m = std::min(e->mb1, n - f0);
-    if ((rc = run_first(e, e->det_first, frames ? frames + (size_t)f0 * H * W : nullptr,
-                        images ? images + (size_t)f0 * H * W : nullptr, a0, m, H, W, e->conv_impl == DCU_CONV_TCGEN05, s)))
-      return rc;                                                                                                // conv1a
-    if ((rc = run_3x3(e, e->det[0], e->conv_impl, a0, a1, m, H, W, nullptr, s))) return rc;                     // conv1b + pool
+  // conv1a is HBM-write bound (19.7 MB per frame), conv1b/2a/2b are tensor bound: run conv1a of micro-batch i+1 on a side
+  // stream while the tensor-core kernels of micro-batch i run on the caller's stream (double-buffered conv1a output).
+  const bool h2 = e->conv_impl == DCU_CONV_TCGEN05;
+  const int n_mb = (n + e->mb1 - 1) / e->mb1;
+  const bool overlap = e->overlap_first && n_mb > 1 && !e->profiling;
+  auto first = [&](int i, cudaStream_t st) -> int {
+    const int f0 = i * e->mb1, m = std::min(e->mb1, n - f0);
+    return run_first(e, e->det_first, frames ? frames + (size_t)f0 * H * W : nullptr,
+                     images ? images + (size_t)f0 * H * W : nullptr, e->c1[i & 1].as<float>(), m, H, W, h2, st);
+  };
+  if (overlap) {
+    CK(cudaEventRecord(e->ev_start, s));
+    CK(cudaStreamWaitEvent(e->side, e->ev_start, 0));        // inputs (e.g. the H2D copy) are ordered on the caller's stream
+    if ((rc = first(0, e->side))) return rc;
+    CK(cudaEventRecord(e->ev_done[0], e->side));
+  }
+  for (int i = 0; i < n_mb; ++i) {
+    const int f0 = i * e->mb1, m = std::min(e->mb1, n - f0);
+    float* c1 = e->c1[i & 1].as<float>();
+    if (overlap) {
+      if (i + 1 < n_mb) {
+        if (i >= 1) CK(cudaStreamWaitEvent(e->side, e->ev_free[(i + 1) & 1], 0));   // conv1b of micro-batch i-1 has read that buffer
+        if ((rc = first(i + 1, e->side))) return rc;
+        CK(cudaEventRecord(e->ev_done[(i + 1) & 1], e->side));
+      }
+      CK(cudaStreamWaitEvent(s, e->ev_done[i & 1], 0));
+    } else {
+      if ((rc = first(i, s))) return rc;                                                                         // conv1a
+    }
+    if ((rc = run_3x3(e, e->det[0], e->conv_impl, c1, a1, m, H, W, nullptr, s))) return rc;                     // conv1b + pool
+    if (overlap) CK(cudaEventRecord(e->ev_free[i & 1], s));
     if ((rc = run_3x3(e, e->det[1], e->conv_impl, a1, a0, m, H / 2, W / 2, nullptr, s))) return rc;             // conv2a
     if ((rc = run_3x3(e, e->det[2], e->conv_impl, a0, s2 + f0 * s2_frame, m, H / 2, W / 2, nullptr, s))) return rc;  // conv2b + pool
   }
@@ -555,6 +588,15 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   const size_t det_low = (size_t)e->mb2 * 128 * (H / 4) * (W / 4);           // conv3a out
   const size_t ref_big = e->has_ref ? (size_t)e->rp * 64 * 64 * 64 : 0;      // conv5b upsampled
   const size_t act_floats = std::max(std::max(det_full, det_low), ref_big);
+  TRYC(e->c1[0].alloc(det_full * 4));
+  TRYC(e->c1[1].alloc(det_full * 4));
+  TRYC(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+  TRYC(cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) {
+    TRYC(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&e->ev_free[i], cudaEventDisableTiming));
+  }
+  if (const char* v = getenv("DCU_OVERLAP_FIRST")) e->overlap_first = atoi(v) != 0;
   TRYC(e->act[0].alloc(act_floats * 4));
   TRYC(e->act[1].alloc(act_floats * 4));
   TRYC(e->stage2_in.alloc((size_t)e->mb2 * 64 * (H / 4) * (W / 4) * 4));
