@@ -18,7 +18,7 @@ CONV_DEFAULT = CONV_TCGEN05   # tcgen05 tensor-core path (fp16 hi/lo split); CON
 
 EXPORTS = [
     "dcu_create", "dcu_destroy", "dcu_detector_forward", "dcu_detector_forward_f32", "dcu_extract_patches",
-    "dcu_decode_gather", "dcu_refine_forward", "dcu_infer_batch", "dcu_infer_batch_host",
+    "dcu_decode_gather", "dcu_refine_forward", "dcu_infer_batch", "dcu_infer_batch_host", "dcu_infer_batch_host_bgr", "dcu_bgr_to_gray",
     "dcu_debug_conv_layer", "dcu_debug_tc_stats", "dcu_set_conv_impl", "dcu_launch_count", "dcu_profile_enable", "dcu_profile_read", "dcu_detector_flops_per_frame",
     "dcu_refine_flops_per_patch", "dcu_last_error", "dcu_version",
 ]
@@ -67,6 +67,8 @@ def lib():
     L.dcu_refine_forward.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
     L.dcu_infer_batch.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.dcu_infer_batch_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.dcu_infer_batch_host_bgr.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.dcu_bgr_to_gray.argtypes = [vp, vp, i32, vp, vp]
     L.dcu_debug_conv_layer.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]
     L.dcu_debug_tc_stats.argtypes = [vp, i32, vp]
     L.dcu_set_conv_impl.argtypes = [vp, i32]
@@ -220,13 +222,15 @@ class Engine:
         return float(lib().dcu_refine_flops_per_patch(self._h))
 
     def infer_batch_host(self, frames_u8, dust_bin_ids=16, use_refinenet=True, stream=None):
-        """frames_u8: (N,H,W) uint8 host array -> (counts[N], offsets[N], kpts[total,4] int32, refined[total,2] f32 | None).
+        """frames_u8: (N,H,W) grayscale or (N,H,W,3) BGR uint8 host array -> (counts[N], offsets[N], kpts[total,4] int32, refined[total,2] f32 | None).
         H2D, the whole pipeline and D2H happen inside the call (dcu_infer_batch_host)."""
         f = np.ascontiguousarray(frames_u8, dtype=np.uint8)
         n = int(f.shape[0])
-        if f.ndim != 3 or f.shape[1] != self.height or f.shape[2] != self.width:
-            raise ValueError(f"frames must be (N,{self.height},{self.width}) uint8, got {f.shape}")
-        rc = lib().dcu_infer_batch_host(self._h, f.ctypes.data, n, int(dust_bin_ids), 1 if use_refinenet else 0,
+        bgr = f.ndim == 4 and f.shape[3] == 3
+        if f.ndim not in (3, 4) or (f.ndim == 4 and not bgr) or f.shape[1] != self.height or f.shape[2] != self.width:
+            raise ValueError(f"frames must be (N,{self.height},{self.width}) or (N,{self.height},{self.width},3) uint8, got {f.shape}")
+        entry = lib().dcu_infer_batch_host_bgr if bgr else lib().dcu_infer_batch_host
+        rc = entry(self._h, f.ctypes.data, n, int(dust_bin_ids), 1 if use_refinenet else 0,
                                         self._counts.ctypes.data, self._offsets.ctypes.data, C.addressof(self._total),
                                         self._kpts.ctypes.data, self._refined.ctypes.data if use_refinenet else None,
                                         stream)

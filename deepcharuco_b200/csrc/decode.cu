@@ -15,7 +15,7 @@
 
 namespace dcu {
 
-constexpr int D_THREADS = 256;
+constexpr int D_THREADS = 320;   // 300 four-cell quads of a 30x40 cell grid fit one pass
 
 size_t decode_smem_bytes(int cells) { return (size_t)cells * 4 * sizeof(uint32_t); }
 
@@ -41,27 +41,67 @@ decode_gather_kernel(DecodeParams p) {
   __syncthreads();
 
   // ---- phase 1: per-cell arg-max + dustbin filter ------------------------------------------------
+  // Four consecutive cells per thread, one 16-byte load per logit plane: consecutive threads read consecutive 16 B of a
+  // plane (fully coalesced) and every thread keeps 8 planes x 16 B in flight, which is what it takes to cover HBM latency
+  // with one CTA per frame.  Strict '>' keeps the FIRST maximum, as torch.argmax does.
   const float* loc = p.loc + (size_t)f * 65 * cells;
   const float* ids = p.ids + (size_t)f * p.n_ids1 * cells;
-  for (int c = tid; c < cells; c += D_THREADS) {
-    float best = loc[c];
-    int la = 0;
+  if ((cells & 3) == 0) {
+    const int quads = cells >> 2;
+    for (int q = tid; q < quads; q += D_THREADS) {
+      const float4* lp = reinterpret_cast<const float4*>(loc) + q;
+      float4 best = lp[0];
+      int la[4] = {0, 0, 0, 0};
 #pragma unroll 8
-    for (int ch = 1; ch < 65; ++ch) {
-      const float v = loc[(size_t)ch * cells + c];
-      if (v > best) { best = v; la = ch; }        // strict '>' keeps the FIRST maximum (torch.argmax)
+      for (int ch = 1; ch < 65; ++ch) {
+        const float4 v = lp[(size_t)ch * quads];
+        if (v.x > best.x) { best.x = v.x; la[0] = ch; }
+        if (v.y > best.y) { best.y = v.y; la[1] = ch; }
+        if (v.z > best.z) { best.z = v.z; la[2] = ch; }
+        if (v.w > best.w) { best.w = v.w; la[3] = ch; }
+      }
+      const float4* ip = reinterpret_cast<const float4*>(ids) + q;
+      float4 bi = ip[0];
+      int ia[4] = {0, 0, 0, 0};
+#pragma unroll 4
+      for (int ch = 1; ch < p.n_ids1; ++ch) {
+        const float4 v = ip[(size_t)ch * quads];
+        if (v.x > bi.x) { bi.x = v.x; ia[0] = ch; }
+        if (v.y > bi.y) { bi.y = v.y; ia[1] = ch; }
+        if (v.z > bi.z) { bi.z = v.z; ia[2] = ch; }
+        if (v.w > bi.w) { bi.w = v.w; ia[3] = ch; }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int id = (la[e] == 64) ? p.dust_bin : ia[e];     // model_utils.py:77 (loc dustbin hard-coded 64)
+        if (id != p.dust_bin) {                          // model_utils.py:111
+          const int slot = atomicAdd(&s_count, 1);
+          key_u[slot] = (uint32_t)id * (uint32_t)cells + (uint32_t)(4 * q + e);
+          pix_u[slot] = (uint32_t)la[e];
+        }
+      }
     }
-    float bi = ids[c];
-    int ia = 0;
-    for (int ch = 1; ch < p.n_ids1; ++ch) {
-      const float v = ids[(size_t)ch * cells + c];
-      if (v > bi) { bi = v; ia = ch; }
-    }
-    if (la == 64) ia = p.dust_bin;                // model_utils.py:77 (loc dustbin hard-coded 64)
-    if (ia != p.dust_bin) {                        // model_utils.py:111
-      const int slot = atomicAdd(&s_count, 1);
-      key_u[slot] = (uint32_t)ia * (uint32_t)cells + (uint32_t)c;
-      pix_u[slot] = (uint32_t)la;
+  } else {
+    for (int c = tid; c < cells; c += D_THREADS) {
+      float best = loc[c];
+      int la = 0;
+#pragma unroll 8
+      for (int ch = 1; ch < 65; ++ch) {
+        const float v = loc[(size_t)ch * cells + c];
+        if (v > best) { best = v; la = ch; }
+      }
+      float bi = ids[c];
+      int ia = 0;
+      for (int ch = 1; ch < p.n_ids1; ++ch) {
+        const float v = ids[(size_t)ch * cells + c];
+        if (v > bi) { bi = v; ia = ch; }
+      }
+      if (la == 64) ia = p.dust_bin;
+      if (ia != p.dust_bin) {
+        const int slot = atomicAdd(&s_count, 1);
+        key_u[slot] = (uint32_t)ia * (uint32_t)cells + (uint32_t)c;
+        pix_u[slot] = (uint32_t)la;
+      }
     }
   }
   __syncthreads();
@@ -144,6 +184,33 @@ void launch_decode_gather(const DecodeParams& p, cudaStream_t s) {
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(decode_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   decode_gather_kernel<<<p.n, D_THREADS, smem, s>>>(p);
+}
+
+// BGR -> gray on the device (reference: cv2.cvtColor(img, COLOR_BGR2GRAY), inference.py:40).
+// OpenCV's 8-bit path is the fixed-point form  (3735*B + 19235*G + 9798*R + 2^14) >> 15 ; verified against cv2 4.13 on all
+// 2^24 colours (tests/test_host_logic.py).  One thread converts 4 pixels: three 4-byte loads, one 4-byte store.
+__global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray, long long n_px) {
+  const long long n4 = n_px >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(bgr) + i * 3;
+    const uint32_t w0 = src[0], w1 = src[1], w2 = src[2];     // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+    const uint32_t b0 = w0 & 255u, g0 = (w0 >> 8) & 255u, r0 = (w0 >> 16) & 255u;
+    const uint32_t b1 = w0 >> 24, g1 = w1 & 255u, r1 = (w1 >> 8) & 255u;
+    const uint32_t b2 = (w1 >> 16) & 255u, g2 = w1 >> 24, r2 = w2 & 255u;
+    const uint32_t b3 = (w2 >> 8) & 255u, g3 = (w2 >> 16) & 255u, r3 = w2 >> 24;
+    const uint32_t y0 = (3735u * b0 + 19235u * g0 + 9798u * r0 + 16384u) >> 15;
+    const uint32_t y1 = (3735u * b1 + 19235u * g1 + 9798u * r1 + 16384u) >> 15;
+    const uint32_t y2 = (3735u * b2 + 19235u * g2 + 9798u * r2 + 16384u) >> 15;
+    const uint32_t y3 = (3735u * b3 + 19235u * g3 + 9798u * r3 + 16384u) >> 15;
+    reinterpret_cast<uint32_t*>(gray)[i] = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+  }
+}
+void launch_bgr_to_gray(const uint8_t* bgr, uint8_t* gray, long long n_px, cudaStream_t s) {
+  if (n_px <= 0) return;
+  long long b = ((n_px >> 2) + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  if (b < 1) b = 1;
+  bgr_to_gray_kernel<<<(int)b, 256, 0, s>>>(bgr, gray, n_px);
 }
 
 // stand-alone extract_patches on a normalised fp32 image (model_utils.py:19-36)

@@ -190,6 +190,7 @@ struct DcuEngine {
   DevBuf heads;                 // (Pa|Da) output for mb2 frames
   DevBuf loc, ids;              // [mb2] logits when the caller does not want them
   DevBuf counts, offsets, total, kpts, patches, keys, refined, scan_state, frames;
+  DevBuf bgr;                   // [max_batch][H][W][3] staging for the BGR entry point (allocated on first use)
   unsigned int epoch = 1;
   // optional per-launch event timing (dcu_profile_*)
   struct ProfRec { cudaEvent_t a, b; double work; int cls; };
@@ -218,7 +219,7 @@ struct DcuEngine {
     if (side) cudaStreamDestroy(side);
     if (ev_start) cudaEventDestroy(ev_start);
     for (int i = 0; i < 2; ++i) { if (ev_done[i]) cudaEventDestroy(ev_done[i]); if (ev_free[i]) cudaEventDestroy(ev_free[i]); }
-    DevBuf* all[] = {&c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
+    DevBuf* all[] = {&bgr, &c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
                      &ids, &counts, &offsets, &total, &kpts, &patches, &keys, &refined, &scan_state, &frames};
     for (DevBuf* b : all) b->release();
     FirstLayer* fl[] = {&det_first, &ref_first};
@@ -778,27 +779,64 @@ int dcu_infer_batch(DcuEngine* e, const uint8_t* frames_dev, int n, int dust_bin
   return refine_run(e, e->patches.as<float>(), kpts_dev, 4, total, nullptr, refined_dev, nullptr, s);
 }
 
+int dcu_bgr_to_gray(DcuEngine* e, const uint8_t* bgr_dev, int n, uint8_t* gray_dev, void* stream) {
+  if (!e || !bgr_dev || !gray_dev || n < 0) return fail(DCU_ERR_INVALID, "dcu_bgr_to_gray: bad argument");
+  CK(cudaSetDevice(e->cfg.device));
+  launch_bgr_to_gray(bgr_dev, gray_dev, (long long)n * e->cfg.height * e->cfg.width, (cudaStream_t)stream);
+  e->launches++;
+  CK(cudaGetLastError());
+  return DCU_OK;
+}
+
+static int infer_batch_host_impl(DcuEngine* e, const uint8_t* frames_host, int n, int channels, int dust_bin_ids, int use_refinenet,
+                                 int32_t* counts_host, int32_t* offsets_host, int32_t* total_host, int32_t* kpts_host,
+                                 float* refined_host, void* stream);
+
 int dcu_infer_batch_host(DcuEngine* e, const uint8_t* frames_host, int n, int dust_bin_ids, int use_refinenet,
                          int32_t* counts_host, int32_t* offsets_host, int32_t* total_host, int32_t* kpts_host,
                          float* refined_host, void* stream) {
+  return infer_batch_host_impl(e, frames_host, n, 1, dust_bin_ids, use_refinenet, counts_host, offsets_host, total_host, kpts_host,
+                               refined_host, stream);
+}
+
+int dcu_infer_batch_host_bgr(DcuEngine* e, const uint8_t* frames_host, int n, int dust_bin_ids, int use_refinenet,
+                             int32_t* counts_host, int32_t* offsets_host, int32_t* total_host, int32_t* kpts_host,
+                             float* refined_host, void* stream) {
+  return infer_batch_host_impl(e, frames_host, n, 3, dust_bin_ids, use_refinenet, counts_host, offsets_host, total_host, kpts_host,
+                               refined_host, stream);
+}
+
+static int infer_batch_host_impl(DcuEngine* e, const uint8_t* frames_host, int n, int channels, int dust_bin_ids, int use_refinenet,
+                                 int32_t* counts_host, int32_t* offsets_host, int32_t* total_host, int32_t* kpts_host,
+                                 float* refined_host, void* stream) {
   if (!e || !frames_host || !counts_host || !offsets_host || !total_host || !kpts_host || n < 0)
     return fail(DCU_ERR_INVALID, "dcu_infer_batch_host: bad argument");
   if (n > e->cfg.max_batch) return fail(DCU_ERR_INVALID, "dcu_infer_batch_host: n > max_batch");
   if (use_refinenet && !refined_host) return fail(DCU_ERR_INVALID, "dcu_infer_batch_host: refined_host is NULL");
   CK(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t fbytes = (size_t)n * e->cfg.height * e->cfg.width;
+  const size_t gbytes = (size_t)n * e->cfg.height * e->cfg.width;
+  const size_t fbytes = gbytes * channels;
   *total_host = 0;
   if (n == 0) return DCU_OK;
-  // stage through the engine's pinned buffer unless the caller's memory is already pinned
+  if (channels == 3 && e->bgr.p == nullptr) CK(e->bgr.alloc((size_t)e->cfg.max_batch * e->cfg.height * e->cfg.width * 3));
+  // stage through the engine's pinned buffer unless the caller's memory is already pinned (BGR: pageable copies are used as is)
   const uint8_t* src = frames_host;
   cudaPointerAttributes pa;
-  if (cudaPointerGetAttributes(&pa, frames_host) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+  if (channels == 1 && (cudaPointerGetAttributes(&pa, frames_host) != cudaSuccess || pa.type != cudaMemoryTypeHost)) {
     cudaGetLastError();
     std::memcpy(e->h_frames, frames_host, fbytes);
     src = e->h_frames;
   }
-  CK(cudaMemcpyAsync(e->frames.p, src, fbytes, cudaMemcpyHostToDevice, s));
+  cudaGetLastError();
+  if (channels == 3) {
+    CK(cudaMemcpyAsync(e->bgr.p, src, fbytes, cudaMemcpyHostToDevice, s));
+    launch_bgr_to_gray(e->bgr.as<uint8_t>(), e->frames.as<uint8_t>(), (long long)gbytes, s);
+    e->launches++;
+    CK(cudaGetLastError());
+  } else {
+    CK(cudaMemcpyAsync(e->frames.p, src, fbytes, cudaMemcpyHostToDevice, s));
+  }
   int rc = dcu_infer_batch(e, e->frames.as<uint8_t>(), n, dust_bin_ids, use_refinenet, e->counts.as<int32_t>(),
                            e->offsets.as<int32_t>(), e->total.as<int32_t>(), e->kpts.as<int32_t>(),
                            e->refined.as<float>(), s);

@@ -191,15 +191,13 @@ def _rows_to_frames(counts, offsets, kpts, refined):
 
 
 def infer_batch(frames, dust_bin_ids: int, deepc: DeepcHandle, refinenet: Optional[RefineHandle] = None):
-    """Batched form of infer_image: frames (N,H,W) uint8 grayscale (or (N,H,W,3) BGR) -> list of N keypoint arrays.
+    """Batched form of infer_image: frames (N,H,W) uint8 grayscale or (N,H,W,3) BGR -> list of N keypoint arrays.
 
     One H2D copy of the u8 frames, the fused GPU pipeline, one D2H copy of the packed result."""
     frames = np.asarray(frames)
-    if frames.ndim == 4:
-        import cv2
-        frames = np.stack([cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in frames])
-    assert frames.ndim == 3 and frames.dtype == np.uint8, "frames must be (N,H,W) uint8"
-    n, H, W = frames.shape
+    assert frames.dtype == np.uint8 and (frames.ndim == 3 or (frames.ndim == 4 and frames.shape[3] == 3)), \
+        "frames must be (N,H,W) grayscale or (N,H,W,3) BGR uint8"
+    n, H, W = frames.shape[:3]          # BGR frames are converted on the device (OpenCV's fixed-point luma, bit-exact)
     if H % 8 or W % 8:
         raise ValueError(f"frame size {W}x{H} must be a multiple of 8 (three 2x2 pools, net.py:62,65,68)")
     if n == 0:

@@ -134,6 +134,15 @@ int dcu_infer_batch_host(DcuEngine* e, const uint8_t* frames_host, int n, int du
                          int32_t* counts_host, int32_t* offsets_host, int32_t* total_host,
                          int32_t* kpts_host, float* refined_host, void* stream);
 
+/* Replaces cv2.cvtColor(img, COLOR_BGR2GRAY) (inference.py:40) on the device: bgr_dev uint8 [N][H][W][3] -> gray_dev uint8
+ * [N][H][W], OpenCV's 8-bit fixed-point luma, bit-exact.  (SURVEY.md 8f "next" row 1.) */
+int dcu_bgr_to_gray(DcuEngine* e, const uint8_t* bgr_dev, int n, uint8_t* gray_dev, void* stream);
+
+/* dcu_infer_batch_host for BGR frames: frames_host uint8 [N][H][W][3]; the colour conversion runs on the device too. */
+int dcu_infer_batch_host_bgr(DcuEngine* e, const uint8_t* frames_host, int n, int dust_bin_ids, int use_refinenet,
+                             int32_t* counts_host, int32_t* offsets_host, int32_t* total_host,
+                             int32_t* kpts_host, float* refined_host, void* stream);
+
 /* Test hook: run ONE 3x3 conv(+BN+ReLU[+pool][+2x nearest up]) layer of either network on fp32 NCHW
  * device tensors with the selected implementation (DCU_CONV_*), so each layer is checkable against
  * the oracle in isolation.  net: 0 detector, 1 RefineNet; layer: index into the dcu_create tables.

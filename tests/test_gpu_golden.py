@@ -104,6 +104,30 @@ def test_640x480(models, golden_640):
         _check_refined(got, w)
 
 
+def test_bgr_batch_equals_gray_batch(models, golden_sample, golden_synth):
+    """(N,H,W,3) BGR frames: colour conversion on the device must equal cv2.cvtColor bit for bit, hence identical results."""
+    import cv2
+    import torch
+    from deepcharuco_b200 import _native as N
+    deepc, refinenet = models
+    rng = np.random.default_rng(3)
+    gray = golden_synth["frames"][:4]
+    bgr = np.stack([cv2.cvtColor(f, cv2.COLOR_GRAY2BGR) for f in gray])
+    bgr = np.clip(bgr.astype(np.int16) + rng.integers(-20, 21, bgr.shape), 0, 255).astype(np.uint8)     # real colour content
+    bgr = np.concatenate([bgr, golden_sample["bgr"][None]], 0)
+    want_gray = np.stack([cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in bgr])
+    eng = deepc._ctx.engine(240, 320, max_batch=8)
+    d_bgr = torch.from_numpy(bgr).cuda()
+    d_gray = torch.empty((5, 240, 320), dtype=torch.uint8, device="cuda")
+    N.check(N.lib().dcu_bgr_to_gray(eng.handle, d_bgr.data_ptr(), 5, d_gray.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(d_gray.cpu().numpy(), want_gray)
+    a = dc.infer_batch(bgr, 16, deepc, refinenet)
+    b = dc.infer_batch(want_gray, 16, deepc, refinenet)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    _check_refined(a[4], golden_sample["out_refined"])
+
+
 def test_empty_batch_and_bad_shapes(models):
     deepc, refinenet = models
     assert dc.infer_batch(np.zeros((0, 240, 320), np.uint8), 16, deepc, refinenet) == []

@@ -84,3 +84,14 @@ def test_pack_unpack_round_trip():
     c, f = sharding.pack_results(res)
     back = sharding.unpack_results(c, f)
     assert all(np.array_equal(a, b) for a, b in zip(res, back))
+
+
+def test_bgr_to_gray_fixed_point_matches_cv2():
+    """The device kernel's formula (csrc/decode.cu: bgr_to_gray_kernel) is OpenCV's 8-bit luma; pin it against cv2 itself."""
+    import cv2
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (240, 320, 3)).astype(np.uint8)
+    img[:16, :16] = np.array([[b, g, 255 - b] for b in range(16) for g in range(0, 256, 16)], np.uint8).reshape(16, 16, 3)
+    B, G, R = (img[..., i].astype(np.int64) for i in range(3))
+    got = ((3735 * B + 19235 * G + 9798 * R + 16384) >> 15).astype(np.uint8)
+    assert np.array_equal(got, cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
