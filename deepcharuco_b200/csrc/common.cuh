@@ -113,6 +113,11 @@ void tc_tile_arrangement(int nt, int hout, int wout, int* tr, int* tc);
 cudaError_t launch_conv3x3_tc(const ConvParams& p, const float* w_blocks, int n_slices, int w_copies, const void* tmap_in,
                               int sm_count, cudaStream_t s);
 
+// CTA-pair (cta_group::2) variant, conv_tc2.cu
+int tc2_block_bytes(int nt);
+cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, const void* tmap_a, const void* tmap_w0, const void* tmap_w1,
+                            int sm_count, cudaStream_t s);
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace dcu

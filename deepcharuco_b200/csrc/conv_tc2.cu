@@ -1,0 +1,516 @@
+// CTA-pair (cta_group::2) variant of the tcgen05 convolution kernel in conv_tc.cu.
+//
+// Same math, layouts and epilogue as conv_tc.cu (read its header first).  What changes: two CTAs of a cluster (one TPC)
+// work on two adjacent CTA tiles with ONE stream of MMAs of M = 256 issued by the leader CTA.  Each CTA supplies the
+// A rows (pixels) of its own tile from its own shared memory, but only HALF of the weight rows: conv_tc.cu is bound by
+// the tensor core's operand fetch from shared memory (~0.33 cycles per 32-byte operand row), and in a pair the B operand
+// is fetched once per two m-tiles.  Per (tap, 16-channel chunk, m-tile) a CTA fetches 128 + NT rows for a_hi x [w_hi|w_lo]
+// and 128 + NT/2 rows for a_lo x w_hi instead of 128 + 2*NT and 128 + NT.
+//
+// Weight blocks are packed per CTA rank (engine.cu: pack_tc_pair):
+//   rank 0:  main = w_hi rows [0,NT)   | X = w_hi rows [0,NT/2)
+//   rank 1:  main = w_lo rows [0,NT)   | X = w_hi rows [NT/2,NT)
+// so that a_hi x [main0 ; main1] = [a_hi*w_hi | a_hi*w_lo] (N' = 2*NT) and a_lo x [X0 ; X1] = a_lo*w_hi (N = NT), with the
+// same shared-memory offsets in both CTAs (one descriptor addresses both halves).
+//
+// Protocol (after cutlass/pipeline/sm100_pipeline.hpp, PipelineTmaUmmaAsync with a 2-SM MMA):
+//   * every barrier exists in both CTAs at the same offset; "full" barriers are only waited on in the leader: both CTAs'
+//     TMA loads (.cta_group::2) complete_tx on the LEADER's barrier, the leader's producer arms it for 2x the bytes;
+//   * "empty" / acc_full barriers are released by tcgen05.commit.cta_group::2 ... multicast::cluster with mask 0b11, i.e. they
+//     fire in both CTAs, so each CTA's producers and epilogue wait on their local copy;
+//   * acc_empty lives in the leader and counts the epilogue threads of BOTH CTAs (remote mbarrier.arrive via mapa).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace dcu {
+
+namespace {
+
+constexpr int T2_THREADS = 384;
+
+template <int NT>
+struct Tc2Cfg {
+  static constexpr int MT = 2;
+  static constexpr int NBUF = 512 / (MT * 2 * NT);
+  static constexpr int A_STAGES = 4;
+  static constexpr int B_STAGES = (NT == 64) ? 6 : 4;
+  static constexpr int MAX_HALO_PX = 34 * 10;
+  static constexpr int A_STAGE_BYTES = 4 * MAX_HALO_PX * 16;
+  static constexpr int B_MAIN_BYTES = 2 * NT * 16;                 // 2 k-groups x NT rows x 8 fp16 (this rank's half of [w_hi | w_lo])
+  static constexpr int B_X_BYTES = 2 * (NT / 2) * 16;              // 2 k-groups x NT/2 rows     (this rank's half of w_hi)
+  static constexpr int B_BLOCK_BYTES = B_MAIN_BYTES + B_X_BYTES;   // 48 * NT
+  static constexpr int B_STAGE_BYTES = 3 * B_BLOCK_BYTES;          // up to 3 taps per stage
+  static constexpr int PARAM_BYTES = 3 * 512 * 4;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
+};
+
+struct Tc2Geo {
+  int tr, tc, halo_w, halo_h, tiles_x, tiles_y, slices;
+  long long tiles_per_slice, pairs_per_slice, total_pairs;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in the even (leader) CTA of the pair
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 remAddr32;\n"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+template <int kBackoffNs = 0>
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (kBackoffNs > 0) __nanosleep(kBackoffNs);
+    if (clock64() - t0 > 4000000000LL) __trap();      // a protocol bug must fail the launch, never hang the GPU box
+  }
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+// both CTAs execute these; the transaction bytes are credited to the LEADER's barrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                                int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma2_f16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// commit: arrive (once) on the barrier at this offset in BOTH CTAs when all prior MMAs of the pair have retired
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .b16 m;\n"
+      "mov.b16 m, 3;\n"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, float* a, uint32_t tb, float* b) {
+  tmem_ld16_nowait(ta, a);
+  tmem_ld16_nowait(tb, b);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  x0 = fminf(x0, 65504.f); x1 = fminf(x1, 65504.f);
+  const __half2 hh = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
+__device__ __forceinline__ void store_h2_16(uint4* hi_plane0, size_t lo_offset, size_t kg_stride, const float* v) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_h2(v[8 * k + 2 * e], v[8 * k + 2 * e + 1], h[e], l[e]);
+    hi_plane0[(size_t)k * kg_stride] = make_uint4(h[0], h[1], h[2], h[3]);
+    hi_plane0[(size_t)k * kg_stride + lo_offset] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+__device__ __forceinline__ unsigned int orderable(float v) {
+  unsigned int b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+struct Tile2 { int img, slice, y0, x0; bool valid; };
+__device__ __forceinline__ Tile2 decode_pair_tile(long long pt, uint32_t rank, const Tc2Geo& g) {
+  Tile2 c;
+  c.slice = (int)(pt / g.pairs_per_slice);
+  long long t = (pt - (long long)c.slice * g.pairs_per_slice) * 2 + rank;
+  c.valid = t < g.tiles_per_slice;
+  if (!c.valid) t = g.tiles_per_slice - 1;            // odd tail: the peer recomputes the last tile and discards it
+  const int tx = (int)(t % g.tiles_x); t /= g.tiles_x;
+  const int ty = (int)(t % g.tiles_y);
+  c.img = (int)(t / g.tiles_y);
+  c.y0 = ty * 16 * g.tr;
+  c.x0 = tx * 8 * g.tc;
+  return c;
+}
+
+template <int NT, int KS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w0,
+                const __grid_constant__ CUtensorMap tmap_w1, const ConvParams p, const Tc2Geo g) {
+  using Cfg = Tc2Cfg<NT>;
+  constexpr int MT = Cfg::MT, NBUF = Cfg::NBUF, B_STAGES = Cfg::B_STAGES;
+  constexpr int ROWS = KS, TPR = KS, TAPS = KS * KS;
+  constexpr int ROWS_PER_BLOCK = Cfg::B_BLOCK_BYTES / 512;          // weight tensor map rows (512 B each) per block
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* a_smem = smem_raw;
+  uint8_t* b_smem = a_smem + Cfg::A_STAGES * Cfg::A_STAGE_BYTES;
+  float* prm = reinterpret_cast<float*>(b_smem + B_STAGES * Cfg::B_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(prm) + Cfg::PARAM_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + Cfg::A_STAGES;
+  uint64_t* b_full = a_empty + Cfg::A_STAGES;
+  uint64_t* b_empty = b_full + B_STAGES;
+  uint64_t* acc_full = b_empty + B_STAGES;
+  uint64_t* acc_empty = acc_full + NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NBUF * MT);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int chunks = p.cin >> 4;
+  const int halo_px = g.halo_w * g.halo_h;
+
+  for (int i = threadIdx.x; i < p.cout_total; i += T2_THREADS) {
+    prm[i] = p.bias[i];
+    prm[512 + i] = p.alpha[i];
+    prm[1024 + i] = p.beta[i];
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < NBUF; ++i) mbar_init(&acc_full[i], 1);
+    for (int i = 0; i < NBUF * MT; ++i) mbar_init(&acc_empty[i], 256);      // epilogue threads of both CTAs (leader's copy is used)
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                 // barriers of BOTH CTAs initialised before anyone signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ================= activation producer: this CTA's halo into this CTA's smem, bytes credited to the leader =================
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    int st = 0; uint32_t ph = 0;
+    for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
+      const Tile2 c = decode_pair_tile(pt, rank, g);
+      for (int q = 0; q < chunks; ++q) {
+        mbar_wait<200>(&a_empty[st], ph ^ 1u);
+        if (rank == 0) mbar_expect_tx(&a_full[st], 2u * (uint32_t)halo_px * 64u);
+        tma_load_5d_2sm(smem_u32(a_smem + (size_t)st * Cfg::A_STAGE_BYTES), &tmap_a, &a_full[st], (c.x0 - p.pad) * 8, c.y0 - p.pad,
+                        (p.cin_offset >> 3) + q * 2, 0, c.img);
+        if (++st == Cfg::A_STAGES) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 2 && lane == 0) {
+    // ================= weight producer: this rank's half blocks (2-D tensor map over 512-byte rows) =================
+    const CUtensorMap* wm = rank ? &tmap_w1 : &tmap_w0;
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(wm)) : "memory");
+    int st = 0; uint32_t ph = 0;
+    for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
+      const int slice = (int)(pt / g.pairs_per_slice);
+      const int blk0 = slice * chunks * TAPS;
+      for (int blk = 0; blk < chunks * TAPS; blk += TPR) {
+        mbar_wait<200>(&b_empty[st], ph ^ 1u);
+        if (rank == 0) mbar_expect_tx(&b_full[st], 2u * (uint32_t)(TPR * Cfg::B_BLOCK_BYTES));
+        tma_load_2d_2sm(smem_u32(b_smem + (size_t)st * Cfg::B_STAGE_BYTES), wm, &b_full[st], 0, (blk0 + blk) * ROWS_PER_BLOCK);
+        if (++st == B_STAGES) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ================= MMA issuer (leader CTA only): M = 256 spans both CTAs' m-tiles =================
+    constexpr uint32_t IDESC_BASE = (1u << 4) | (0u << 7) | (0u << 10) | (16u << 24);    // f32 accum, f16 x f16, K-major, M = 256
+    constexpr uint32_t IDESC_2N = IDESC_BASE | ((uint32_t)((2 * NT) >> 3) << 17);
+    constexpr uint32_t IDESC_1N = IDESC_BASE | ((uint32_t)(NT >> 3) << 17);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a_desc_hi = (uint32_t)g.halo_w | (1u << 14);                 // SBO = halo_w * 16 B
+    const uint32_t a_desc_lo0 = ((uint32_t)halo_px << 16);                      // LBO = plane
+    constexpr uint32_t b_desc_hi = 8u | (1u << 14);                             // SBO = 128 B
+    constexpr uint32_t bm_desc_lo0 = ((uint32_t)NT << 16);                      // main half: NT rows per k-group
+    constexpr uint32_t bx_desc_lo0 = ((uint32_t)(NT / 2) << 16);                // X half: NT/2 rows per k-group
+    const uint32_t a_base0 = (smem_u32(a_smem) & 0x3FFFFu) >> 4, b_base0 = (smem_u32(b_smem) & 0x3FFFFu) >> 4;
+    uint32_t mt_off[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int tri = mt / g.tc, tci = mt - tri * g.tc;
+      mt_off[mt] = (uint32_t)(tri * 16 * g.halo_w + tci * 8);
+    }
+    int sa = 0, sb = 0, buf = 0; uint32_t pha = 0, phb = 0, phc = 0;
+    for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
+      for (int q = 0; q < chunks; ++q) {
+        mbar_wait(&a_full[sa], pha);
+        tc_fence_after();
+        const uint32_t a_hi = a_desc_lo0 + a_base0 + (uint32_t)sa * (Cfg::A_STAGE_BYTES >> 4);
+        if (q == 0) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) mbar_wait(&acc_empty[buf * MT + mt], phc ^ 1u);
+          tc_fence_after();
+        }
+#pragma unroll 1
+        for (int ky = 0; ky < ROWS; ++ky) {
+          mbar_wait(&b_full[sb], phb);
+          tc_fence_after();
+          const uint32_t a_row = a_hi + (uint32_t)(ky * g.halo_w);
+          const uint32_t b_row = b_base0 + (uint32_t)sb * (Cfg::B_STAGE_BYTES >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int kx = 0; kx < TPR; ++kx) {
+              const uint32_t b_main = bm_desc_lo0 + b_row + (uint32_t)kx * (Cfg::B_BLOCK_BYTES >> 4);
+              const uint32_t b_x = bx_desc_lo0 + b_row + (uint32_t)kx * (Cfg::B_BLOCK_BYTES >> 4) + (uint32_t)(Cfg::B_MAIN_BYTES >> 4);
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t d = tmem_u + (uint32_t)((buf * MT + mt) * 2 * NT);
+                const uint32_t da_hi = a_row + (uint32_t)kx + mt_off[mt];
+                const uint32_t da_lo = da_hi + 2u * (uint32_t)halo_px;
+                umma2_f16_w(d, da_hi, a_desc_hi, b_main, b_desc_hi, IDESC_2N, (q | ky | kx) ? 1u : 0u);   // [a_hi*w_hi | a_hi*w_lo]
+                umma2_f16_w(d + NT, da_lo, a_desc_hi, b_x, b_desc_hi, IDESC_1N, 1u);                        // + a_lo*w_hi
+              }
+            }
+            umma2_commit_mc(&b_empty[sb]);
+            if (ky == ROWS - 1) umma2_commit_mc(&a_empty[sa]);
+            if (ky == ROWS - 1 && q == chunks - 1) umma2_commit_mc(&acc_full[buf]);
+          }
+          __syncwarp();
+          if (++sb == B_STAGES) { sb = 0; phb ^= 1u; }
+        }
+        if (++sa == Cfg::A_STAGES) { sa = 0; pha ^= 1u; }
+      }
+      if (++buf == NBUF) { buf = 0; phc ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (both CTAs, each drains its own 128 TMEM lanes) =================
+    constexpr int CW = 16;
+    const int grp = (warp >= 8) ? 1 : 0;
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;
+    const int prow = m >> 3, pcol = m & 7;
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const int c8_out = p.cout_total >> 3;
+    uint32_t phc = 0;
+    int buf = 0;
+    for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
+      const Tile2 c = decode_pair_tile(pt, rank, g);
+      mbar_wait<200>(&acc_full[buf], phc);
+      tc_fence_after();
+      const int ch_base = c.slice * NT;
+#pragma unroll 1
+      for (int mt = grp; mt < MT; mt += 2) {
+        const int tri = mt / g.tc, tci = mt - tri * g.tc;
+        const int oy = c.y0 + tri * 16 + prow, ox = c.x0 + tci * 8 + pcol;
+        const bool inb = c.valid && (oy < p.hout) && (ox < p.wout);
+        float head_sum = 0.f;
+#pragma unroll 1
+        for (int cc = 0; cc < NT / CW; ++cc) {
+          float v[CW];
+          {
+            float sm[CW];
+            const uint32_t col = (uint32_t)((buf * MT + mt) * 2 * NT + cc * CW);
+            tmem_ld16x2(tmem_base + lane_addr + col, v, tmem_base + lane_addr + col + NT, sm);
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] = (v[j] + sm[j]) * p.wscale_inv;
+          }
+          const int ch0 = ch_base + cc * CW;
+          if (p.logits != nullptr) {
+            if (inb) {
+              const size_t plane_o = (size_t)p.hout * p.wout;
+              float* o = p.logits + (size_t)c.img * p.n_valid * plane_o + (size_t)oy * p.wout + ox;
+#pragma unroll
+              for (int j = 0; j < CW; ++j)
+                if (ch0 + j < p.n_valid) o[(size_t)(ch0 + j) * plane_o] = v[j] + prm[ch0 + j];
+            }
+            continue;
+          }
+#pragma unroll
+          for (int j = 0; j < CW; j += 4) {
+            const float4 bi = *reinterpret_cast<const float4*>(&prm[ch0 + j]);
+            const float4 al = *reinterpret_cast<const float4*>(&prm[512 + ch0 + j]);
+            const float4 be = *reinterpret_cast<const float4*>(&prm[1024 + ch0 + j]);
+            v[j + 0] = fmaxf(fmaf(v[j + 0] + bi.x, al.x, be.x), 0.0f);
+            v[j + 1] = fmaxf(fmaf(v[j + 1] + bi.y, al.y, be.y), 0.0f);
+            v[j + 2] = fmaxf(fmaf(v[j + 2] + bi.z, al.z, be.z), 0.0f);
+            v[j + 3] = fmaxf(fmaf(v[j + 3] + bi.w, al.w, be.w), 0.0f);
+          }
+          if (p.head_w != nullptr) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) head_sum = fmaf(v[j], __ldg(p.head_w + cc * CW + j), head_sum);
+          } else if (p.pool) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+              float x = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+              v[j] = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
+            }
+            const int hp = p.hout >> 1, wp = p.wout >> 1;
+            if (c.valid && ((lane & 9) == 0) && (oy >> 1) < hp && (ox >> 1) < wp) {
+              const size_t plane_o = (size_t)hp * wp;
+              uint4* o = reinterpret_cast<uint4*>(p.out) + ((size_t)c.img * 2 * c8_out + (ch0 >> 3)) * plane_o + (size_t)(oy >> 1) * wp + (ox >> 1);
+              store_h2_16(o, (size_t)c8_out * plane_o, plane_o, v);
+            }
+          } else if (p.ups) {
+            if (inb) {
+              const int hu = p.hout * 2, wu = p.wout * 2;
+              const size_t plane_o = (size_t)hu * wu;
+              uint4* o = reinterpret_cast<uint4*>(p.out) + ((size_t)c.img * 2 * c8_out + (ch0 >> 3)) * plane_o + (size_t)(2 * oy) * wu + 2 * ox;
+              const size_t lo_off = (size_t)c8_out * plane_o;
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_h2(v[8 * k + 2 * e], v[8 * k + 2 * e + 1], h[e], l[e]);
+                const uint4 hv = make_uint4(h[0], h[1], h[2], h[3]), lv = make_uint4(l[0], l[1], l[2], l[3]);
+                uint4* ok = o + (size_t)k * plane_o;
+                ok[0] = hv; ok[1] = hv; ok[wu] = hv; ok[wu + 1] = hv;
+                ok[lo_off] = lv; ok[lo_off + 1] = lv; ok[lo_off + wu] = lv; ok[lo_off + wu + 1] = lv;
+              }
+            }
+          } else {
+            if (inb) {
+              const size_t plane_o = (size_t)p.hout * p.wout;
+              uint4* o = reinterpret_cast<uint4*>(p.out) + ((size_t)c.img * 2 * c8_out + (ch0 >> 3)) * plane_o + (size_t)oy * p.wout + ox;
+              store_h2_16(o, (size_t)c8_out * plane_o, plane_o, v);
+            }
+          }
+        }
+        if (p.head_w != nullptr) {
+          const float s = head_sum + p.head_b;
+          unsigned long long key = 0ull;
+          if (inb) {
+            const unsigned int idx = (unsigned)(oy * p.wout + ox);
+            if (p.heat != nullptr) p.heat[(size_t)c.img * p.hout * p.wout + idx] = s;
+            key = ((unsigned long long)orderable(s) << 32) | (unsigned long long)(~idx);
+          }
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
+          }
+          if (lane == 0 && key != 0ull) atomicMax(p.head_key + c.img, key);
+        }
+        tc_fence_before();
+        mbar_arrive_cluster(&acc_empty[buf * MT + mt], 0);      // always the leader's barrier
+      }
+      if (++buf == NBUF) { buf = 0; phc ^= 1u; }
+    }
+  }
+
+  // ---- teardown: nobody may exit (or free TMEM) while the peer can still touch this CTA's barriers / tensor memory ----
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <int NT, int KS>
+cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta, const CUtensorMap* w0, const CUtensorMap* w1,
+                        int sm_count, cudaStream_t s) {
+  using Cfg = Tc2Cfg<NT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  Tc2Geo g;
+  tc_tile_arrangement(NT, p.hout, p.wout, &g.tr, &g.tc);
+  g.halo_w = 8 * g.tc + 2; g.halo_h = 16 * g.tr + 2;
+  if (g.halo_w * g.halo_h > Cfg::MAX_HALO_PX) return cudaErrorInvalidValue;
+  g.tiles_x = ceil_div(p.wout, 8 * g.tc); g.tiles_y = ceil_div(p.hout, 16 * g.tr);
+  g.slices = n_slices;
+  g.tiles_per_slice = (long long)p.n * g.tiles_x * g.tiles_y;
+  g.pairs_per_slice = (g.tiles_per_slice + 1) / 2;
+  g.total_pairs = g.pairs_per_slice * g.slices;
+  if (g.total_pairs <= 0) return cudaSuccess;
+  const long long clusters = g.total_pairs < sm_count / 2 ? g.total_pairs : sm_count / 2;
+  conv_tc2_kernel<NT, KS><<<(int)clusters * 2, T2_THREADS, Cfg::SMEM_BYTES, s>>>(*ta, *w0, *w1, p, g);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+int tc2_block_bytes(int nt) { return 48 * nt; }
+
+cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, const void* tmap_a, const void* tmap_w0, const void* tmap_w1,
+                            int sm_count, cudaStream_t s) {
+  const CUtensorMap* ta = reinterpret_cast<const CUtensorMap*>(tmap_a);
+  const CUtensorMap* w0 = reinterpret_cast<const CUtensorMap*>(tmap_w0);
+  const CUtensorMap* w1 = reinterpret_cast<const CUtensorMap*>(tmap_w1);
+  const int nt = p.cout_total / n_slices;
+  if (p.ksize == 1) return cudaErrorInvalidValue;      // the 1x1 heads stay on the single-CTA kernel
+  if (nt == 64) return launch_pair<64, 3>(p, n_slices, ta, w0, w1, sm_count, s);
+  if (nt == 128) return launch_pair<128, 3>(p, n_slices, ta, w0, w1, sm_count, s);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace dcu

@@ -50,6 +50,8 @@ struct Layer3x3 {
   DevBuf w_tc;                // tcgen05 blocks (conv_tc.cu layout), empty if shape unsupported
   float tc_scale = 1.f;       // power-of-two weight scale baked into w_tc
   int tc_copies = 1;          // replicas of w_tc (spread the all-CTA broadcast reads over more L2 slices)
+  DevBuf w_tc2[2];            // CTA-pair packing per rank (conv_tc2.cu)
+  CUtensorMap wmap2[2];       // 2-D tensor maps over w_tc2 (rows of 512 B, box = one 3-tap stage)
   int tc_nt = 0;              // N per CTA pass for the tcgen05 kernel (64 / 128), 0 = unsupported
   DevBuf bias, alpha, beta;   // [cout]
 };
@@ -135,6 +137,49 @@ std::vector<uint16_t> pack_tc(const std::vector<const float*>& ws, const std::ve
   return out;
 }
 
+// CTA-pair packing (conv_tc2.cu): per rank r, block = [main_r: 2 k-groups x NT rows][X_r: 2 k-groups x NT/2 rows] of 8 fp16,
+//   main_0 = w_hi, main_1 = w_lo, X_r = w_hi rows [r*NT/2, (r+1)*NT/2).  Same block order as pack_tc.
+std::vector<uint16_t> pack_tc_pair(const std::vector<const float*>& ws, const std::vector<int>& couts, int cin, int nt, float scale,
+                                   int rank) {
+  int cout_total = 0;
+  for (int c : couts) cout_total += c;
+  const int slices = cout_total / nt, chunks = cin / 16;
+  const size_t main_h = (size_t)2 * nt * 8, x_h = (size_t)2 * (nt / 2) * 8, blk = main_h + x_h;
+  std::vector<uint16_t> out((size_t)slices * chunks * 9 * blk, 0);
+  std::vector<const float*> row(cout_total);
+  {
+    int o = 0;
+    for (size_t t = 0; t < ws.size(); ++t)
+      for (int k = 0; k < couts[t]; ++k) row[o++] = ws[t] + (size_t)k * cin * 9;
+  }
+  auto split = [&](float w, uint16_t& hb, uint16_t& lb) {
+    const float ws_ = w * scale;
+    const __half hi = __float2half_rn(ws_);
+    const __half lo = __float2half_rn(ws_ - __half2float(hi));
+    std::memcpy(&hb, &hi, 2); std::memcpy(&lb, &lo, 2);
+  };
+  for (int s = 0; s < slices; ++s)
+    for (int q = 0; q < chunks; ++q)
+      for (int tap = 0; tap < 9; ++tap) {
+        uint16_t* b = out.data() + (((size_t)s * chunks + q) * 9 + tap) * blk;
+        for (int kg = 0; kg < 2; ++kg)
+          for (int e = 0; e < 8; ++e) {
+            const int ci = q * 16 + kg * 8 + e;
+            for (int n = 0; n < nt; ++n) {
+              uint16_t hb, lb;
+              split(row[s * nt + n][(size_t)ci * 9 + tap], hb, lb);
+              b[((size_t)kg * nt + n) * 8 + e] = rank == 0 ? hb : lb;
+            }
+            for (int n = 0; n < nt / 2; ++n) {
+              uint16_t hb, lb;
+              split(row[s * nt + rank * (nt / 2) + n][(size_t)ci * 9 + tap], hb, lb);
+              b[main_h + ((size_t)kg * (nt / 2) + n) * 8 + e] = hb;
+            }
+          }
+      }
+  return out;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -186,6 +231,7 @@ struct DcuEngine {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_start = nullptr, ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   bool overlap_first = true;
+  bool tc_pair = true;          // use the CTA-pair (cta_group::2) kernel for the 3x3 layers (DCU_TC_PAIR=0: single-CTA kernel)
   DevBuf stage2_in;             // conv2b output for mb2 frames (input of conv3a)
   DevBuf heads;                 // (Pa|Da) output for mb2 frames
   DevBuf loc, ids;              // [mb2] logits when the caller does not want them
@@ -224,8 +270,8 @@ struct DcuEngine {
     for (DevBuf* b : all) b->release();
     FirstLayer* fl[] = {&det_first, &ref_first};
     for (FirstLayer* f : fl) { f->w.release(); f->bias.release(); f->alpha.release(); f->beta.release(); }
-    for (Layer3x3& l : det) { l.w_ffma.release(); l.w_tc.release(); l.bias.release(); l.alpha.release(); l.beta.release(); }
-    for (Layer3x3& l : ref) { l.w_ffma.release(); l.w_tc.release(); l.bias.release(); l.alpha.release(); l.beta.release(); }
+    for (Layer3x3& l : det) { l.w_tc2[0].release(); l.w_tc2[1].release(); l.w_ffma.release(); l.w_tc.release(); l.bias.release(); l.alpha.release(); l.beta.release(); }
+    for (Layer3x3& l : ref) { l.w_tc2[0].release(); l.w_tc2[1].release(); l.w_ffma.release(); l.w_tc.release(); l.bias.release(); l.alpha.release(); l.beta.release(); }
     for (auto& r : prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto ev : ev_pool) cudaEventDestroy(ev);
     if (h_frames) cudaFreeHost(h_frames);
@@ -279,6 +325,22 @@ int build_3x3(Layer3x3& l, std::vector<const DcuConvLayer*> parts, int pad, int 
     CK(l.w_tc.alloc(blocks.size() * 2 * l.tc_copies));
     for (int c = 0; c < l.tc_copies; ++c)
       CK(cudaMemcpy(l.w_tc.as<uint8_t>() + (size_t)c * blocks.size() * 2, blocks.data(), blocks.size() * 2, cudaMemcpyHostToDevice));
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    for (int r = 0; r < 2; ++r) {
+      const std::vector<uint16_t> pb = pack_tc_pair(ws, couts, cin, l.tc_nt, l.tc_scale, r);
+      CK(l.w_tc2[r].alloc(pb.size() * 2));
+      CK(cudaMemcpy(l.w_tc2[r].p, pb.data(), pb.size() * 2, cudaMemcpyHostToDevice));
+      const int rows_per_block = tc2_block_bytes(l.tc_nt) / 512;
+      cuuint64_t dims[2] = {256, (cuuint64_t)(pb.size() * 2 / 512)};
+      cuuint64_t strides[1] = {512};
+      cuuint32_t box[2] = {256, (cuuint32_t)(3 * rows_per_block)};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult cr = enc(&l.wmap2[r], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, l.w_tc2[r].p, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed: " + std::to_string((int)cr));
+    }
   }
   return DCU_OK;
 }
@@ -326,7 +388,9 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
     CUtensorMap tm;
     int rc = make_tmap(&tm, in, n, l.cin, hin, win, 8 * g.tc + 2, 16 * g.tr + 2);
     if (rc) return rc;
-    cudaError_t ce = launch_conv3x3_tc(p, l.w_tc.as<float>(), l.cout / l.tc_nt, l.tc_copies, &tm, e->sm_count, s);
+    cudaError_t ce = e->tc_pair
+                         ? launch_conv_tc2(p, l.cout / l.tc_nt, &tm, &l.wmap2[0], &l.wmap2[1], e->sm_count, s)
+                         : launch_conv3x3_tc(p, l.w_tc.as<float>(), l.cout / l.tc_nt, l.tc_copies, &tm, e->sm_count, s);
     if (ce != cudaSuccess) return fail(DCU_ERR_CUDA, std::string("tcgen05 conv launch: ") + cudaGetErrorString(ce));
   } else {
     launch_conv3x3_ffma(p, l.w_ffma.as<float>(), s);
@@ -598,6 +662,7 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
     TRYC(cudaEventCreateWithFlags(&e->ev_free[i], cudaEventDisableTiming));
   }
   if (const char* v = getenv("DCU_OVERLAP_FIRST")) e->overlap_first = atoi(v) != 0;
+  if (const char* v = getenv("DCU_TC_PAIR")) e->tc_pair = atoi(v) != 0;
   TRYC(e->act[0].alloc(act_floats * 4));
   TRYC(e->act[1].alloc(act_floats * 4));
   TRYC(e->stage2_in.alloc((size_t)e->mb2 * 64 * (H / 4) * (W / 4) * 4));
