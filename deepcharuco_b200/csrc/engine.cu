@@ -239,7 +239,7 @@ struct DcuEngine {
   DevBuf bgr;                   // [max_batch][H][W][3] staging for the BGR entry point (allocated on first use)
   unsigned int epoch = 1;
   // optional per-launch event timing (dcu_profile_*)
-  struct ProfRec { cudaEvent_t a, b; double work; int cls; };
+  struct ProfRec { cudaEvent_t a, b; double work; int cls; int shape[5]; };   // shape: cin, cout, hout, wout, n
   bool profiling = false;
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
@@ -247,9 +247,9 @@ struct DcuEngine {
     if (!ev_pool.empty()) { cudaEvent_t ev = ev_pool.back(); ev_pool.pop_back(); return ev; }
     cudaEvent_t ev; cudaEventCreate(&ev); return ev;
   }
-  void prof_begin(int cls, double work, cudaStream_t s) {
+  void prof_begin(int cls, double work, cudaStream_t s, int cin = 0, int cout = 0, int hout = 0, int wout = 0, int n = 0) {
     if (!profiling) return;
-    ProfRec r{get_event(), get_event(), work, cls};
+    ProfRec r{get_event(), get_event(), work, cls, {cin, cout, hout, wout, n}};
     cudaEventRecord(r.a, s);
     prof.push_back(r);
   }
@@ -381,7 +381,7 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
   p.wscale_inv = (impl == DCU_CONV_TCGEN05) ? 1.0f / l.tc_scale : 1.0f;
   p.ksize = 3;
   if (n <= 0) return DCU_OK;
-  e->prof_begin(0, 2.0 * 9.0 * l.cin * l.cout * (double)p.hout * p.wout * n, s);
+  e->prof_begin(0, 2.0 * 9.0 * l.cin * l.cout * (double)p.hout * p.wout * n, s, l.cin, l.cout, p.hout, p.wout, n);
   if (impl == DCU_CONV_TCGEN05) {
     if (l.tc_nt == 0) return fail(DCU_ERR_UNSUPPORTED, "layer shape not supported by the tcgen05 kernel");
     const TcGeom g = tc_geom(l.tc_nt, p.hout, p.wout);
@@ -409,7 +409,7 @@ static int run_first(DcuEngine* e, const FirstLayer& f, const uint8_t* in_u8, co
   p.bias = f.bias.as<float>(); p.alpha = f.alpha.as<float>(); p.beta = f.beta.as<float>();
   p.n = n; p.hin = hin; p.win = win; p.pad = f.pad; p.hout = hin + 2 * f.pad - 2; p.wout = win + 2 * f.pad - 2;
   if (n <= 0) return DCU_OK;
-  e->prof_begin(1, 2.0 * 9.0 * 64 * (double)p.hout * p.wout * n, s);
+  e->prof_begin(1, 2.0 * 9.0 * 64 * (double)p.hout * p.wout * n, s, 1, 64, p.hout, p.wout, n);
   launch_conv_first(p, s);
   e->prof_end(s);
   e->launches++;
@@ -731,6 +731,25 @@ int dcu_profile_read(DcuEngine* e, int cls, double* total_ms, double* total_work
     ms += t; work += r.work; ++n;
   }
   *total_ms = ms; *total_work = work; *n_launches = n;
+  return DCU_OK;
+}
+
+int dcu_profile_records(DcuEngine* e, int cap, double* rec8, int* n_records) {
+  if (!e || !n_records || (cap > 0 && !rec8)) return fail(DCU_ERR_INVALID, "dcu_profile_records: bad argument");
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaDeviceSynchronize());
+  int i = 0;
+  for (auto& r : e->prof) {
+    if (i < cap) {
+      float t = 0.f;
+      CK(cudaEventElapsedTime(&t, r.a, r.b));
+      double* o = rec8 + (size_t)i * 8;
+      o[0] = r.cls; o[1] = t; o[2] = r.work;
+      for (int k = 0; k < 5; ++k) o[3 + k] = r.shape[k];
+    }
+    ++i;
+  }
+  *n_records = i;
   return DCU_OK;
 }
 

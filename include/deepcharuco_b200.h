@@ -169,6 +169,9 @@ int64_t dcu_launch_count(const DcuEngine* e);
  * ALGORITHMIC work: flops (2*MAC) for classes 0-2, bytes for class 3. */
 int dcu_profile_enable(DcuEngine* e, int on);
 int dcu_profile_read(DcuEngine* e, int cls, double* total_ms, double* total_work, int64_t* n_launches);
+/* The individual records since the last enable, in launch order: rec8 [cap][8] doubles
+ * {cls, ms, work, cin, cout, hout, wout, n}; *n_records = how many exist (may exceed cap). */
+int dcu_profile_records(DcuEngine* e, int cap, double* rec8, int* n_records);
 
 /* Algorithmic FLOPs (2*MAC) per frame of the detector and per patch of RefineNet for this engine's
  * shapes (12.879 GFLOP / 320x240 frame, 0.8711 GFLOP / patch). */
