@@ -100,8 +100,9 @@ void launch_refine_finalize(const unsigned long long* keys, const int32_t* xy, i
 // layout converters used by the debug/test entry point
 void launch_nchw_to_c4(const float* in, float* out, int n, int c, int h, int w, cudaStream_t s);
 void launch_c4_to_nchw(const float* in, float* out, int n, int c, int h, int w, cudaStream_t s);
-void launch_nchw_to_h2(const float* in, void* out, int n, int c, int h, int w, cudaStream_t s);
-void launch_h2_to_nchw(const void* in, float* out, int n, int c, int h, int w, cudaStream_t s);
+// sub: the NCHW input is [h*sub][w*sub] and pixel (y*sub, x*sub) is taken; rep: the NCHW output is [h*rep][w*rep] (nearest)
+void launch_nchw_to_h2(const float* in, void* out, int n, int c, int h, int w, cudaStream_t s, int sub = 1);
+void launch_h2_to_nchw(const void* in, float* out, int n, int c, int h, int w, cudaStream_t s, int rep = 1);
 
 // tcgen05 path (conv_tc.cu)
 struct TcLayerPack {
@@ -115,7 +116,9 @@ cudaError_t launch_conv3x3_tc(const ConvParams& p, const float* w_blocks, int n_
 
 // CTA-pair (cta_group::2) variant, conv_tc2.cu
 int tc2_block_bytes(int nt);
-cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, const void* tmap_a, const void* tmap_w0, const void* tmap_w1,
+int tc2_stage_blocks(int up);       // weight blocks per bulk-copy stage (tensor-map box)
+// up != 0: p.in is the LOW-resolution tensor (hin x win) whose 2x nearest upsampling is the layer's input; hout = 2*hin
+cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const void* tmap_a, const void* tmap_w0, const void* tmap_w1,
                             int sm_count, cudaStream_t s);
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

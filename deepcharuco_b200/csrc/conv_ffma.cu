@@ -455,13 +455,13 @@ __global__ void c4_to_nchw_kernel(const float* in, float* out, int n, int c, int
     out[i] = in[((((size_t)img * (c >> 2) + (ch >> 2)) * h + y) * w + x) * 4 + (ch & 3)];
   }
 }
-__global__ void nchw_to_h2_kernel(const float* in, __half* out, int n, int c, int h, int w) {
+__global__ void nchw_to_h2_kernel(const float* in, __half* out, int n, int c, int h, int w, int sub) {
   const long long total = (long long)n * c * h * w;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % w); long long t = i / w;
     const int y = (int)(t % h); t /= h;
     const int ch = (int)(t % c); const int img = (int)(t / c);
-    const float v = fminf(in[i], 65504.f);
+    const float v = fminf(in[(((size_t)img * c + ch) * (h * sub) + (size_t)y * sub) * (w * sub) + (size_t)x * sub], 65504.f);
     const __half hi = __float2half_rn(v);
     const __half lo = __float2half_rn(v - __half2float(hi));
     const size_t o = ((((size_t)img * 2) * (c >> 3) + (ch >> 3)) * h + y) * w + x;
@@ -469,27 +469,28 @@ __global__ void nchw_to_h2_kernel(const float* in, __half* out, int n, int c, in
     out[(o + (size_t)(c >> 3) * h * w) * 8 + (ch & 7)] = lo;
   }
 }
-__global__ void h2_to_nchw_kernel(const __half* in, float* out, int n, int c, int h, int w) {
-  const long long total = (long long)n * c * h * w;
+__global__ void h2_to_nchw_kernel(const __half* in, float* out, int n, int c, int h, int w, int rep) {
+  const int ho = h * rep, wo = w * rep;
+  const long long total = (long long)n * c * ho * wo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % w); long long t = i / w;
-    const int y = (int)(t % h); t /= h;
+    const int x = (int)(i % wo) / rep; long long t = i / wo;
+    const int y = (int)(t % ho) / rep; t /= ho;
     const int ch = (int)(t % c); const int img = (int)(t / c);
     const size_t o = ((((size_t)img * 2) * (c >> 3) + (ch >> 3)) * h + y) * w + x;
     out[i] = __half2float(in[o * 8 + (ch & 7)]) + __half2float(in[(o + (size_t)(c >> 3) * h * w) * 8 + (ch & 7)]);
   }
 }
-void launch_nchw_to_h2(const float* in, void* out, int n, int c, int h, int w, cudaStream_t s) {
+void launch_nchw_to_h2(const float* in, void* out, int n, int c, int h, int w, cudaStream_t s, int sub) {
   const long long total = (long long)n * c * h * w;
   if (total <= 0) return;
   long long b = (total + 255) / 256; if (b > 148 * 16) b = 148 * 16;
-  nchw_to_h2_kernel<<<(int)b, 256, 0, s>>>(in, reinterpret_cast<__half*>(out), n, c, h, w);
+  nchw_to_h2_kernel<<<(int)b, 256, 0, s>>>(in, reinterpret_cast<__half*>(out), n, c, h, w, sub);
 }
-void launch_h2_to_nchw(const void* in, float* out, int n, int c, int h, int w, cudaStream_t s) {
-  const long long total = (long long)n * c * h * w;
+void launch_h2_to_nchw(const void* in, float* out, int n, int c, int h, int w, cudaStream_t s, int rep) {
+  const long long total = (long long)n * c * h * w * rep * rep;
   if (total <= 0) return;
   long long b = (total + 255) / 256; if (b > 148 * 16) b = 148 * 16;
-  h2_to_nchw_kernel<<<(int)b, 256, 0, s>>>(reinterpret_cast<const __half*>(in), out, n, c, h, w);
+  h2_to_nchw_kernel<<<(int)b, 256, 0, s>>>(reinterpret_cast<const __half*>(in), out, n, c, h, w, rep);
 }
 
 void launch_nchw_to_c4(const float* in, float* out, int n, int c, int h, int w, cudaStream_t s) {

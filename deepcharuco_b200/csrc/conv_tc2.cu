@@ -30,9 +30,10 @@ namespace {
 
 constexpr int T2_THREADS = 384;
 
-template <int NT>
+template <int NT, bool UP = false>
 struct Tc2Cfg {
   static constexpr int MT = 2;
+  static constexpr int STAGE_BLOCKS = UP ? 4 : 3;                  // weight blocks per stage (one kernel row; UP: 2 taps x 2 column phases)
   static constexpr int NBUF = 512 / (MT * 2 * NT);
   static constexpr int A_STAGES = 4;
   static constexpr int B_STAGES = (NT == 64) ? 6 : 4;
@@ -41,7 +42,7 @@ struct Tc2Cfg {
   static constexpr int B_MAIN_BYTES = 2 * NT * 16;                 // 2 k-groups x NT rows x 8 fp16 (this rank's half of [w_hi | w_lo])
   static constexpr int B_X_BYTES = 2 * (NT / 2) * 16;              // 2 k-groups x NT/2 rows     (this rank's half of w_hi)
   static constexpr int B_BLOCK_BYTES = B_MAIN_BYTES + B_X_BYTES;   // 48 * NT
-  static constexpr int B_STAGE_BYTES = 3 * B_BLOCK_BYTES;          // up to 3 taps per stage
+  static constexpr int B_STAGE_BYTES = STAGE_BLOCKS * B_BLOCK_BYTES;
   static constexpr int PARAM_BYTES = 3 * 512 * 4;
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
@@ -210,13 +211,15 @@ __device__ __forceinline__ Tile2 decode_pair_tile(long long pt, uint32_t rank, c
   return c;
 }
 
-template <int NT, int KS>
+template <int NT, int KS, bool UP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w0,
                 const __grid_constant__ CUtensorMap tmap_w1, const ConvParams p, const Tc2Geo g) {
-  using Cfg = Tc2Cfg<NT>;
+  using Cfg = Tc2Cfg<NT, UP>;
   constexpr int MT = Cfg::MT, NBUF = Cfg::NBUF, B_STAGES = Cfg::B_STAGES;
-  constexpr int ROWS = KS, TPR = KS, TAPS = KS * KS;
+  // UP (input = 2x nearest upsampling of the tensor in HBM): per output phase (a, b) the 3x3 taps collapse to 2x2 taps on
+  // the low-resolution tensor, so a weight stage is one of 2 kernel rows = 2 taps x 2 column phases (see header).
+  constexpr int ROWS = UP ? 2 : KS, TPR = UP ? 2 : KS, SB = Cfg::STAGE_BLOCKS, TAPS = ROWS * SB;
   constexpr int ROWS_PER_BLOCK = Cfg::B_BLOCK_BYTES / 512;          // weight tensor map rows (512 B each) per block
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* a_smem = smem_raw;
@@ -281,9 +284,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
       const int slice = (int)(pt / g.pairs_per_slice);
       const int blk0 = slice * chunks * TAPS;
-      for (int blk = 0; blk < chunks * TAPS; blk += TPR) {
+      for (int blk = 0; blk < chunks * TAPS; blk += SB) {
         mbar_wait<200>(&b_empty[st], ph ^ 1u);
-        if (rank == 0) mbar_expect_tx(&b_full[st], 2u * (uint32_t)(TPR * Cfg::B_BLOCK_BYTES));
+        if (rank == 0) mbar_expect_tx(&b_full[st], 2u * (uint32_t)(SB * Cfg::B_BLOCK_BYTES));
         tma_load_2d_2sm(smem_u32(b_smem + (size_t)st * Cfg::B_STAGE_BYTES), wm, &b_full[st], 0, (blk0 + blk) * ROWS_PER_BLOCK);
         if (++st == B_STAGES) { st = 0; ph ^= 1u; }
       }
@@ -308,6 +311,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     int sa = 0, sb = 0, buf = 0; uint32_t pha = 0, phb = 0, phc = 0;
     for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
+      const uint32_t ph_a = UP ? (uint32_t)((pt / g.pairs_per_slice) & 1) : 0u;     // row phase of this work item
       for (int q = 0; q < chunks; ++q) {
         mbar_wait(&a_full[sa], pha);
         tc_fence_after();
@@ -321,17 +325,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         for (int ky = 0; ky < ROWS; ++ky) {
           mbar_wait(&b_full[sb], phb);
           tc_fence_after();
-          const uint32_t a_row = a_hi + (uint32_t)(ky * g.halo_w);
+          const uint32_t a_row = a_hi + (uint32_t)((ky + (int)ph_a) * g.halo_w);
           const uint32_t b_row = b_base0 + (uint32_t)sb * (Cfg::B_STAGE_BYTES >> 4);
           if (elect_one()) {
 #pragma unroll
             for (int kx = 0; kx < TPR; ++kx) {
-              const uint32_t b_main = bm_desc_lo0 + b_row + (uint32_t)kx * (Cfg::B_BLOCK_BYTES >> 4);
-              const uint32_t b_x = bx_desc_lo0 + b_row + (uint32_t)kx * (Cfg::B_BLOCK_BYTES >> 4) + (uint32_t)(Cfg::B_MAIN_BYTES >> 4);
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
+                // UP: m-tile mt is column phase b = mt of the same low-resolution tile: its own weight block, A window shifted by b
+                const uint32_t blk = UP ? (uint32_t)(kx * 2 + mt) : (uint32_t)kx;
+                const uint32_t b_main = bm_desc_lo0 + b_row + blk * (Cfg::B_BLOCK_BYTES >> 4);
+                const uint32_t b_x = bx_desc_lo0 + b_row + blk * (Cfg::B_BLOCK_BYTES >> 4) + (uint32_t)(Cfg::B_MAIN_BYTES >> 4);
                 const uint32_t d = tmem_u + (uint32_t)((buf * MT + mt) * 2 * NT);
-                const uint32_t da_hi = a_row + (uint32_t)kx + mt_off[mt];
+                const uint32_t da_hi = a_row + (uint32_t)kx + (UP ? (uint32_t)mt : mt_off[mt]);
                 const uint32_t da_lo = da_hi + 2u * (uint32_t)halo_px;
                 umma2_f16_w(d, da_hi, a_desc_hi, b_main, b_desc_hi, IDESC_2N, (q | ky | kx) ? 1u : 0u);   // [a_hi*w_hi | a_hi*w_lo]
                 umma2_f16_w(d + NT, da_lo, a_desc_hi, b_x, b_desc_hi, IDESC_1N, 1u);                        // + a_lo*w_hi
@@ -363,11 +369,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const Tile2 c = decode_pair_tile(pt, rank, g);
       mbar_wait<200>(&acc_full[buf], phc);
       tc_fence_after();
-      const int ch_base = c.slice * NT;
+      const int ch_base = (UP ? (c.slice >> 1) : c.slice) * NT;
 #pragma unroll 1
       for (int mt = grp; mt < MT; mt += 2) {
-        const int tri = mt / g.tc, tci = mt - tri * g.tc;
-        const int oy = c.y0 + tri * 16 + prow, ox = c.x0 + tci * 8 + pcol;
+        int oy, ox;
+        if (UP) {        // low-resolution pixel (y0 + prow, x0 + pcol), output phase (slice & 1, mt)
+          oy = 2 * (c.y0 + prow) + (c.slice & 1); ox = 2 * (c.x0 + pcol) + mt;
+        } else {
+          const int tri = mt / g.tc, tci = mt - tri * g.tc;
+          oy = c.y0 + tri * 16 + prow; ox = c.x0 + tci * 8 + pcol;
+        }
         const bool inb = c.valid && (oy < p.hout) && (ox < p.wout);
         float head_sum = 0.f;
 #pragma unroll 1
@@ -472,44 +483,59 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
-template <int NT, int KS>
+template <int NT, int KS, bool UP>
 cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta, const CUtensorMap* w0, const CUtensorMap* w1,
                         int sm_count, cudaStream_t s) {
-  using Cfg = Tc2Cfg<NT>;
+  using Cfg = Tc2Cfg<NT, UP>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NT, KS, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   Tc2Geo g;
-  tc_tile_arrangement(NT, p.hout, p.wout, &g.tr, &g.tc);
-  g.halo_w = 8 * g.tc + 2; g.halo_h = 16 * g.tr + 2;
+  if (UP) {
+    // tiles of 16 x 8 LOW-resolution pixels; the two m-tiles are the column phases; slices = channel slices x 2 row phases
+    if (p.pad != 1 || p.pool || p.ups || p.hout != 2 * p.hin || p.wout != 2 * p.win) return cudaErrorInvalidValue;
+    g.tr = 1; g.tc = 1;
+    g.halo_w = 10; g.halo_h = 18;
+    g.tiles_x = ceil_div(p.win, 8); g.tiles_y = ceil_div(p.hin, 16);
+    n_slices *= 2;
+  } else {
+    tc_tile_arrangement(NT, p.hout, p.wout, &g.tr, &g.tc);
+    g.halo_w = 8 * g.tc + 2; g.halo_h = 16 * g.tr + 2;
+    g.tiles_x = ceil_div(p.wout, 8 * g.tc); g.tiles_y = ceil_div(p.hout, 16 * g.tr);
+  }
   if (g.halo_w * g.halo_h > Cfg::MAX_HALO_PX) return cudaErrorInvalidValue;
-  g.tiles_x = ceil_div(p.wout, 8 * g.tc); g.tiles_y = ceil_div(p.hout, 16 * g.tr);
   g.slices = n_slices;
   g.tiles_per_slice = (long long)p.n * g.tiles_x * g.tiles_y;
   g.pairs_per_slice = (g.tiles_per_slice + 1) / 2;
   g.total_pairs = g.pairs_per_slice * g.slices;
   if (g.total_pairs <= 0) return cudaSuccess;
   const long long clusters = g.total_pairs < sm_count / 2 ? g.total_pairs : sm_count / 2;
-  conv_tc2_kernel<NT, KS><<<(int)clusters * 2, T2_THREADS, Cfg::SMEM_BYTES, s>>>(*ta, *w0, *w1, p, g);
+  conv_tc2_kernel<NT, KS, UP><<<(int)clusters * 2, T2_THREADS, Cfg::SMEM_BYTES, s>>>(*ta, *w0, *w1, p, g);
   return cudaGetLastError();
 }
 
 }  // namespace
 
 int tc2_block_bytes(int nt) { return 48 * nt; }
+int tc2_stage_blocks(int up) { return up ? 4 : 3; }
 
-cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, const void* tmap_a, const void* tmap_w0, const void* tmap_w1,
+cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const void* tmap_a, const void* tmap_w0, const void* tmap_w1,
                             int sm_count, cudaStream_t s) {
   const CUtensorMap* ta = reinterpret_cast<const CUtensorMap*>(tmap_a);
   const CUtensorMap* w0 = reinterpret_cast<const CUtensorMap*>(tmap_w0);
   const CUtensorMap* w1 = reinterpret_cast<const CUtensorMap*>(tmap_w1);
   const int nt = p.cout_total / n_slices;
   if (p.ksize == 1) return cudaErrorInvalidValue;      // the 1x1 heads stay on the single-CTA kernel
-  if (nt == 64) return launch_pair<64, 3>(p, n_slices, ta, w0, w1, sm_count, s);
-  if (nt == 128) return launch_pair<128, 3>(p, n_slices, ta, w0, w1, sm_count, s);
+  if (up) {
+    if (nt == 64) return launch_pair<64, 3, true>(p, n_slices, ta, w0, w1, sm_count, s);
+    if (nt == 128) return launch_pair<128, 3, true>(p, n_slices, ta, w0, w1, sm_count, s);
+    return cudaErrorInvalidValue;
+  }
+  if (nt == 64) return launch_pair<64, 3, false>(p, n_slices, ta, w0, w1, sm_count, s);
+  if (nt == 128) return launch_pair<128, 3, false>(p, n_slices, ta, w0, w1, sm_count, s);
   return cudaErrorInvalidValue;
 }
 

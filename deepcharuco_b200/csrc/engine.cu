@@ -52,6 +52,10 @@ struct Layer3x3 {
   int tc_copies = 1;          // replicas of w_tc (spread the all-CTA broadcast reads over more L2 slices)
   DevBuf w_tc2[2];            // CTA-pair packing per rank (conv_tc2.cu)
   CUtensorMap wmap2[2];       // 2-D tensor maps over w_tc2 (rows of 512 B, box = one 3-tap stage)
+  bool ups_in = false;        // the layer's input is the 2x nearest upsampling of the previous layer's output (refinenet.py:66,71,76)
+  DevBuf w_up[2];             // CTA-pair packing of the phase-collapsed 2x2 weights (pack_tc_pair_up), when ups_in
+  CUtensorMap wmap_up[2];
+  float up_scale = 1.f;
   int tc_nt = 0;              // N per CTA pass for the tcgen05 kernel (64 / 128), 0 = unsupported
   DevBuf bias, alpha, beta;   // [cout]
 };
@@ -180,6 +184,67 @@ std::vector<uint16_t> pack_tc_pair(const std::vector<const float*>& ws, const st
   return out;
 }
 
+// Upsample-fused layers (conv_tc2.cu, UP mode).  With U[i][j] = L[i>>1][j>>1] (UpsamplingNearest2d(2), refinenet.py:66,71,76)
+// the 3x3 convolution of U at output pixel (2y+a, 2x+b) touches only the 2x2 low-resolution pixels
+// L[y+a-1+ky][x+b-1+kx], ky,kx in {0,1}, with the kernel rows / columns that land on the same pixel summed:
+//   a = 0: ky=0 <- row 0,  ky=1 <- rows 1+2;      a = 1: ky=0 <- rows 0+1,  ky=1 <- row 2      (same for b and columns)
+// (zero padding of U at -1 / 2H is zero padding of L at -1 / H).  4 MACs per output instead of 9; the sums are formed in
+// double and then split into fp16 hi/lo like every other weight (22 bits).
+// Blocks: index ((((cslice*2 + a)*chunks + q)*2 + ky)*2 + kx)*2 + b, each in the pack_tc_pair format for `rank`.
+std::vector<double> collapse_up_weights(const float* w, int cout, int cin) {
+  // -> [a][b][ky][kx][o][ci]
+  std::vector<double> c((size_t)16 * cout * cin, 0.0);
+  const int lo[2][2] = {{0, 1}, {0, 2}}, hi[2][2] = {{0, 2}, {1, 2}};   // [phase][k] -> kernel index range [lo, hi]
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b)
+      for (int ky = 0; ky < 2; ++ky)
+        for (int kx = 0; kx < 2; ++kx)
+          for (int o = 0; o < cout; ++o)
+            for (int ci = 0; ci < cin; ++ci) {
+              double acc = 0.0;
+              for (int r = lo[a][ky]; r <= hi[a][ky]; ++r)
+                for (int cc = lo[b][kx]; cc <= hi[b][kx]; ++cc) acc += (double)w[((size_t)o * cin + ci) * 9 + r * 3 + cc];
+              c[((((size_t)(a * 2 + b) * 2 + ky) * 2 + kx) * cout + o) * cin + ci] = acc;
+            }
+  return c;
+}
+
+std::vector<uint16_t> pack_tc_pair_up(const std::vector<double>& comb, int cout, int cin, int nt, float scale, int rank) {
+  const int cslices = cout / nt, chunks = cin / 16;
+  const size_t main_h = (size_t)2 * nt * 8, x_h = (size_t)2 * (nt / 2) * 8, blk = main_h + x_h;
+  std::vector<uint16_t> out((size_t)cslices * 2 * chunks * 8 * blk, 0);
+  auto split = [&](double w, uint16_t& hb, uint16_t& lb) {
+    const double ws_ = w * (double)scale;
+    const __half hi = __float2half_rn((float)ws_);
+    const __half lo = __float2half_rn((float)(ws_ - (double)__half2float(hi)));
+    std::memcpy(&hb, &hi, 2); std::memcpy(&lb, &lo, 2);
+  };
+  for (int cs = 0; cs < cslices; ++cs)
+    for (int a = 0; a < 2; ++a)
+      for (int q = 0; q < chunks; ++q)
+        for (int ky = 0; ky < 2; ++ky)
+          for (int kx = 0; kx < 2; ++kx)
+            for (int b = 0; b < 2; ++b) {
+              uint16_t* blkp = out.data() + ((((((size_t)cs * 2 + a) * chunks + q) * 2 + ky) * 2 + kx) * 2 + b) * blk;
+              const double* cw = comb.data() + (((size_t)(a * 2 + b) * 2 + ky) * 2 + kx) * cout * cin;
+              for (int kg = 0; kg < 2; ++kg)
+                for (int e = 0; e < 8; ++e) {
+                  const int ci = q * 16 + kg * 8 + e;
+                  for (int n = 0; n < nt; ++n) {
+                    uint16_t hb, lb;
+                    split(cw[(size_t)(cs * nt + n) * cin + ci], hb, lb);
+                    blkp[((size_t)kg * nt + n) * 8 + e] = rank == 0 ? hb : lb;
+                  }
+                  for (int n = 0; n < nt / 2; ++n) {
+                    uint16_t hb, lb;
+                    split(cw[(size_t)(cs * nt + rank * (nt / 2) + n) * cin + ci], hb, lb);
+                    blkp[main_h + ((size_t)kg * (nt / 2) + n) * 8 + e] = hb;
+                  }
+                }
+            }
+  return out;
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -231,6 +296,7 @@ struct DcuEngine {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_start = nullptr, ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   bool overlap_first = true;
+  bool fuse_up = true;          // RefineNet: fold the 2x nearest upsamplings into the consuming convolution (DCU_FUSE_UP=0: materialise)
   bool tc_pair = true;          // use the CTA-pair (cta_group::2) kernel for the 3x3 layers (DCU_TC_PAIR=0: single-CTA kernel)
   DevBuf stage2_in;             // conv2b output for mb2 frames (input of conv3a)
   DevBuf heads;                 // (Pa|Da) output for mb2 frames
@@ -271,7 +337,7 @@ struct DcuEngine {
     FirstLayer* fl[] = {&det_first, &ref_first};
     for (FirstLayer* f : fl) { f->w.release(); f->bias.release(); f->alpha.release(); f->beta.release(); }
     for (Layer3x3& l : det) { l.w_tc2[0].release(); l.w_tc2[1].release(); l.w_ffma.release(); l.w_tc.release(); l.bias.release(); l.alpha.release(); l.beta.release(); }
-    for (Layer3x3& l : ref) { l.w_tc2[0].release(); l.w_tc2[1].release(); l.w_ffma.release(); l.w_tc.release(); l.bias.release(); l.alpha.release(); l.beta.release(); }
+    for (Layer3x3& l : ref) { l.w_up[0].release(); l.w_up[1].release(); l.w_tc2[0].release(); l.w_tc2[1].release(); l.w_ffma.release(); l.w_tc.release(); l.bias.release(); l.alpha.release(); l.beta.release(); }
     for (auto& r : prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto ev : ev_pool) cudaEventDestroy(ev);
     if (h_frames) cudaFreeHost(h_frames);
@@ -299,7 +365,21 @@ int build_first(FirstLayer& f, const DcuConvLayer& L, int pad) {
   return DCU_OK;
 }
 
-int build_3x3(Layer3x3& l, std::vector<const DcuConvLayer*> parts, int pad, int pool, int ups) {
+int encode_weight_map(CUtensorMap* tm, void* base, size_t bytes, int nt, int up) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const int rows_per_block = tc2_block_bytes(nt) / 512;
+  cuuint64_t dims[2] = {256, (cuuint64_t)(bytes / 512)};
+  cuuint64_t strides[1] = {512};
+  cuuint32_t box[2] = {256, (cuuint32_t)(tc2_stage_blocks(up) * rows_per_block)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed: " + std::to_string((int)cr));
+  return DCU_OK;
+}
+
+int build_3x3(Layer3x3& l, std::vector<const DcuConvLayer*> parts, int pad, int pool, int ups, bool ups_in = false) {
   std::vector<const float*> ws, bs, as, es;
   std::vector<int> couts;
   int cin = parts[0]->cin;
@@ -325,21 +405,25 @@ int build_3x3(Layer3x3& l, std::vector<const DcuConvLayer*> parts, int pad, int 
     CK(l.w_tc.alloc(blocks.size() * 2 * l.tc_copies));
     for (int c = 0; c < l.tc_copies; ++c)
       CK(cudaMemcpy(l.w_tc.as<uint8_t>() + (size_t)c * blocks.size() * 2, blocks.data(), blocks.size() * 2, cudaMemcpyHostToDevice));
-    PFN_encodeTiled enc = get_encode();
-    if (!enc) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    int rc;
     for (int r = 0; r < 2; ++r) {
       const std::vector<uint16_t> pb = pack_tc_pair(ws, couts, cin, l.tc_nt, l.tc_scale, r);
       CK(l.w_tc2[r].alloc(pb.size() * 2));
       CK(cudaMemcpy(l.w_tc2[r].p, pb.data(), pb.size() * 2, cudaMemcpyHostToDevice));
-      const int rows_per_block = tc2_block_bytes(l.tc_nt) / 512;
-      cuuint64_t dims[2] = {256, (cuuint64_t)(pb.size() * 2 / 512)};
-      cuuint64_t strides[1] = {512};
-      cuuint32_t box[2] = {256, (cuuint32_t)(3 * rows_per_block)};
-      cuuint32_t estr[2] = {1, 1};
-      CUresult cr = enc(&l.wmap2[r], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, l.w_tc2[r].p, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (cr != CUDA_SUCCESS) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled (weights) failed: " + std::to_string((int)cr));
+      if ((rc = encode_weight_map(&l.wmap2[r], l.w_tc2[r].p, pb.size() * 2, l.tc_nt, 0))) return rc;
+    }
+    if (ups_in && parts.size() == 1 && pad == 1 && !pool && !ups) {
+      const std::vector<double> comb = collapse_up_weights(ws[0], l.cout, cin);
+      double mx = 0.0;
+      for (double v : comb) mx = std::max(mx, std::fabs(v));
+      l.up_scale = mx > 0.0 ? (float)std::exp2(std::floor(std::log2(32768.0 / mx))) : 1.f;
+      for (int r = 0; r < 2; ++r) {
+        const std::vector<uint16_t> pb = pack_tc_pair_up(comb, l.cout, cin, l.tc_nt, l.up_scale, r);
+        CK(l.w_up[r].alloc(pb.size() * 2));
+        CK(cudaMemcpy(l.w_up[r].p, pb.data(), pb.size() * 2, cudaMemcpyHostToDevice));
+        if ((rc = encode_weight_map(&l.wmap_up[r], l.w_up[r].p, pb.size() * 2, l.tc_nt, 1))) return rc;
+      }
+      l.ups_in = true;
     }
   }
   return DCU_OK;
@@ -370,15 +454,19 @@ static int make_tmap(CUtensorMap* tm, const void* base, int n, int cin, int h, i
 struct HeadFuse { const float* w = nullptr; float b = 0.f; unsigned long long* keys = nullptr; float* heat = nullptr; };
 static unsigned long long* g_tc_stats = nullptr;   // device [8]; set by dcu_debug_tc_stats (profiling only)
 
+// hin x win: the layer's input size as the reference sees it.  fuse_up (tcgen05 pair kernel only): the upsampling between a
+// producer (l.ups) and its consumer (l.ups_in) is not materialised -- the producer stores its low-resolution output and the
+// consumer runs the phase-collapsed 2x2 kernels on it (`in` is then the hin/2 x win/2 tensor).
 static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, float* out, int n, int hin, int win,
-                   const HeadFuse* hf, cudaStream_t s) {
+                   const HeadFuse* hf, cudaStream_t s, bool fuse_up = false) {
+  const bool up_in = fuse_up && l.ups_in;
   ConvParams p{};
   p.in = in; p.out = out; p.bias = l.bias.as<float>(); p.alpha = l.alpha.as<float>(); p.beta = l.beta.as<float>();
-  p.n = n; p.cin = l.cin; p.cout_total = l.cout; p.hin = hin; p.win = win;
-  p.hout = hin + 2 * l.pad - 2; p.wout = win + 2 * l.pad - 2; p.pad = l.pad; p.pool = l.pool; p.ups = l.ups;
+  p.n = n; p.cin = l.cin; p.cout_total = l.cout; p.hin = up_in ? hin / 2 : hin; p.win = up_in ? win / 2 : win;
+  p.hout = hin + 2 * l.pad - 2; p.wout = win + 2 * l.pad - 2; p.pad = l.pad; p.pool = l.pool; p.ups = fuse_up ? 0 : l.ups;
   if (hf) { p.head_w = hf->w; p.head_b = hf->b; p.head_key = hf->keys; p.heat = hf->heat; }
   p.stats = g_tc_stats;
-  p.wscale_inv = (impl == DCU_CONV_TCGEN05) ? 1.0f / l.tc_scale : 1.0f;
+  p.wscale_inv = (impl == DCU_CONV_TCGEN05) ? 1.0f / (up_in ? l.up_scale : l.tc_scale) : 1.0f;
   p.ksize = 3;
   if (n <= 0) return DCU_OK;
   e->prof_begin(0, 2.0 * 9.0 * l.cin * l.cout * (double)p.hout * p.wout * n, s, l.cin, l.cout, p.hout, p.wout, n);
@@ -386,10 +474,13 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
     if (l.tc_nt == 0) return fail(DCU_ERR_UNSUPPORTED, "layer shape not supported by the tcgen05 kernel");
     const TcGeom g = tc_geom(l.tc_nt, p.hout, p.wout);
     CUtensorMap tm;
-    int rc = make_tmap(&tm, in, n, l.cin, hin, win, 8 * g.tc + 2, 16 * g.tr + 2);
+    int rc = up_in ? make_tmap(&tm, in, n, l.cin, p.hin, p.win, 10, 18)
+                   : make_tmap(&tm, in, n, l.cin, hin, win, 8 * g.tc + 2, 16 * g.tr + 2);
     if (rc) return rc;
+    if (fuse_up && !e->tc_pair) return fail(DCU_ERR_INVALID, "upsample fusion needs the CTA-pair kernel");
     cudaError_t ce = e->tc_pair
-                         ? launch_conv_tc2(p, l.cout / l.tc_nt, &tm, &l.wmap2[0], &l.wmap2[1], e->sm_count, s)
+                         ? (up_in ? launch_conv_tc2(p, l.cout / l.tc_nt, 1, &tm, &l.wmap_up[0], &l.wmap_up[1], e->sm_count, s)
+                                  : launch_conv_tc2(p, l.cout / l.tc_nt, 0, &tm, &l.wmap2[0], &l.wmap2[1], e->sm_count, s))
                          : launch_conv3x3_tc(p, l.w_tc.as<float>(), l.cout / l.tc_nt, l.tc_copies, &tm, e->sm_count, s);
     if (ce != cudaSuccess) return fail(DCU_ERR_CUDA, std::string("tcgen05 conv launch: ") + cudaGetErrorString(ce));
   } else {
@@ -533,16 +624,19 @@ static int refine_run(DcuEngine* e, const float* patches, const int32_t* xy, int
     if ((rc = run_3x3(e, e->ref[0], e->conv_impl, a0, a1, m, 22, 22, nullptr, s))) return rc;   // conv1b -> 20
     if ((rc = run_3x3(e, e->ref[1], e->conv_impl, a1, a0, m, 20, 20, nullptr, s))) return rc;   // conv2a -> 18
     if ((rc = run_3x3(e, e->ref[2], e->conv_impl, a0, a1, m, 18, 18, nullptr, s))) return rc;   // conv2b -> 16 -> pool 8
-    if ((rc = run_3x3(e, e->ref[3], e->conv_impl, a1, a0, m, 8, 8, nullptr, s))) return rc;     // conv3a
-    if ((rc = run_3x3(e, e->ref[4], e->conv_impl, a0, a1, m, 8, 8, nullptr, s))) return rc;     // conv3b -> up 16
-    if ((rc = run_3x3(e, e->ref[5], e->conv_impl, a1, a0, m, 16, 16, nullptr, s))) return rc;   // conv4a
-    if ((rc = run_3x3(e, e->ref[6], e->conv_impl, a0, a1, m, 16, 16, nullptr, s))) return rc;   // conv4b -> up 32
-    if ((rc = run_3x3(e, e->ref[7], e->conv_impl, a1, a0, m, 32, 32, nullptr, s))) return rc;   // conv5a
-    if ((rc = run_3x3(e, e->ref[8], e->conv_impl, a0, a1, m, 32, 32, nullptr, s))) return rc;   // conv5b -> up 64
+    // tcgen05 pair kernel: the three 2x upsamplings are never materialised (run_3x3: fuse_up)
+    const bool fu = e->fuse_up && e->tc_pair && e->conv_impl == DCU_CONV_TCGEN05 && e->ref[5].ups_in && e->ref[7].ups_in &&
+                    e->ref[9].ups_in;
+    if ((rc = run_3x3(e, e->ref[3], e->conv_impl, a1, a0, m, 8, 8, nullptr, s))) return rc;         // conv3a
+    if ((rc = run_3x3(e, e->ref[4], e->conv_impl, a0, a1, m, 8, 8, nullptr, s, fu))) return rc;     // conv3b -> up 16
+    if ((rc = run_3x3(e, e->ref[5], e->conv_impl, a1, a0, m, 16, 16, nullptr, s, fu))) return rc;   // conv4a
+    if ((rc = run_3x3(e, e->ref[6], e->conv_impl, a0, a1, m, 16, 16, nullptr, s, fu))) return rc;   // conv4b -> up 32
+    if ((rc = run_3x3(e, e->ref[7], e->conv_impl, a1, a0, m, 32, 32, nullptr, s, fu))) return rc;   // conv5a
+    if ((rc = run_3x3(e, e->ref[8], e->conv_impl, a0, a1, m, 32, 32, nullptr, s, fu))) return rc;   // conv5b -> up 64
     HeadFuse hf;
     hf.w = e->ref_head_w.as<float>(); hf.b = e->ref_head_b; hf.keys = keys;
     hf.heat = heat ? heat + (size_t)p0 * 4096 : nullptr;
-    if ((rc = run_3x3(e, e->ref[9], e->conv_impl, a1, nullptr, m, 64, 64, &hf, s))) return rc;  // convPa + convPb + arg-max
+    if ((rc = run_3x3(e, e->ref[9], e->conv_impl, a1, nullptr, m, 64, 64, &hf, s, fu))) return rc;  // convPa + convPb + arg-max
     e->prof_begin(4, 0.0, s);
     launch_refine_finalize(keys, xy + (size_t)p0 * xy_stride, xy_stride, m, corners ? corners + 2 * (size_t)p0 : nullptr,
                            refined + 2 * (size_t)p0, s);
@@ -620,7 +714,7 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
     const int rpad[10] = {0, 0, 0, 1, 1, 1, 1, 1, 1, 1};
     const int rpool[10] = {0, 0, 1, 0, 0, 0, 0, 0, 0, 0};
     const int rups[10] = {0, 0, 0, 0, 1, 0, 1, 0, 1, 0};
-    for (int i = 0; i < 10; ++i) TRY(build_3x3(e->ref[i], {&R[1 + i]}, rpad[i], rpool[i], rups[i]));
+    for (int i = 0; i < 10; ++i) TRY(build_3x3(e->ref[i], {&R[1 + i]}, rpad[i], rpool[i], rups[i], i > 0 && rups[i - 1]));
     if (R[11].ksize != 1 || R[11].cin != 64 || R[11].cout != 1 || R[10].cout != 64) {
       delete e;
       return fail(DCU_ERR_INVALID, "dcu_create: RefineNet head shape");
@@ -663,6 +757,7 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   }
   if (const char* v = getenv("DCU_OVERLAP_FIRST")) e->overlap_first = atoi(v) != 0;
   if (const char* v = getenv("DCU_TC_PAIR")) e->tc_pair = atoi(v) != 0;
+  if (const char* v = getenv("DCU_FUSE_UP")) e->fuse_up = atoi(v) != 0;
   TRYC(e->act[0].alloc(act_floats * 4));
   TRYC(e->act[1].alloc(act_floats * 4));
   TRYC(e->stage2_in.alloc((size_t)e->mb2 * 64 * (H / 4) * (W / 4) * 4));
@@ -995,15 +1090,19 @@ int dcu_debug_conv_layer(DcuEngine* e, int net, int layer, int conv_impl, const 
   CK(tout.alloc((size_t)n * cout * hf * wf * 4));
   int rc = DCU_OK;
   const bool h2 = !fl && conv_impl == DCU_CONV_TCGEN05;     // the tcgen05 kernel reads and writes the H2 layout
+  // upsample fusion (run_3x3): the consumer takes the low-resolution tensor, the producer stores one
+  const bool fu = h2 && e->fuse_up && e->tc_pair && (l->ups_in || l->ups);
   if (fl) {
     rc = run_first(e, *fl, nullptr, in_dev, tout.as<float>(), n, h, w, 0, s);
   } else {
-    if (h2) launch_nchw_to_h2(in_dev, tin.p, n, cin, h, w, s);
+    if (h2 && fu && l->ups_in) launch_nchw_to_h2(in_dev, tin.p, n, cin, h / 2, w / 2, s, 2);
+    else if (h2) launch_nchw_to_h2(in_dev, tin.p, n, cin, h, w, s);
     else launch_nchw_to_c4(in_dev, tin.as<float>(), n, cin, h, w, s);
-    rc = run_3x3(e, *l, conv_impl, tin.as<float>(), tout.as<float>(), n, h, w, nullptr, s);
+    rc = run_3x3(e, *l, conv_impl, tin.as<float>(), tout.as<float>(), n, h, w, nullptr, s, fu);
   }
   if (rc == DCU_OK) {
-    if (h2) launch_h2_to_nchw(tout.p, out_dev, n, cout, hf, wf, s);
+    if (h2 && fu && l->ups) launch_h2_to_nchw(tout.p, out_dev, n, cout, ho, wo, s, 2);
+    else if (h2) launch_h2_to_nchw(tout.p, out_dev, n, cout, hf, wf, s);
     else launch_c4_to_nchw(tout.as<float>(), out_dev, n, cout, hf, wf, s);
     cudaError_t ce = cudaStreamSynchronize(s);
     if (ce != cudaSuccess) rc = fail(DCU_ERR_CUDA, std::string("dcu_debug_conv_layer: ") + cudaGetErrorString(ce));

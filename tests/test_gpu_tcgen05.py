@@ -32,8 +32,11 @@ SHAPES = [  # net, layer, cin, h, w, cout, out_h, out_w
     (0, 5, 128, 60, 80, 128, 30, 40), (0, 6, 128, 30, 40, 128, 30, 40), (0, 8, 128, 30, 40, 512, 30, 40),
     (1, 1, 64, 22, 22, 64, 20, 20), (1, 2, 64, 20, 20, 128, 18, 18), (1, 3, 128, 18, 18, 128, 8, 8),
     (1, 4, 128, 8, 8, 128, 8, 8), (1, 5, 128, 8, 8, 128, 16, 16), (1, 6, 128, 16, 16, 128, 16, 16),
-    (1, 8, 128, 32, 32, 64, 32, 32), (1, 9, 64, 32, 32, 64, 64, 64), (1, 10, 64, 64, 64, 64, 64, 64),
+    (1, 7, 128, 16, 16, 128, 32, 32), (1, 8, 128, 32, 32, 64, 32, 32), (1, 9, 64, 32, 32, 64, 64, 64), (1, 10, 64, 64, 64, 64, 64, 64),
 ]
+# RefineNet layers whose input is always a 2x nearest upsampling (refinenet.py:66,71,76): the tcgen05 path folds the upsampling
+# into the convolution (2x2 phase kernels on the low-resolution tensor), so they are tested on upsampled inputs
+UPSAMPLED_INPUT = {(1, 6), (1, 8), (1, 10)}
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -41,7 +44,11 @@ def test_layer_tcgen05_matches_fp32_kernel(engine, shape):
     net, layer, cin, h, w, cout, oh, ow = shape
     rng = np.random.default_rng(layer * 7 + net)
     n = 3
-    x = torch.from_numpy(np.maximum(rng.standard_normal((n, cin, h, w)).astype(np.float32), 0)).cuda()
+    if (net, layer) in UPSAMPLED_INPUT:
+        x = np.maximum(rng.standard_normal((n, cin, h // 2, w // 2)).astype(np.float32), 0).repeat(2, axis=2).repeat(2, axis=3)
+        x = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    else:
+        x = torch.from_numpy(np.maximum(rng.standard_normal((n, cin, h, w)).astype(np.float32), 0)).cuda()
     outs = []
     for impl in (N.CONV_FFMA, N.CONV_TCGEN05):
         out = torch.full((n, cout, oh, ow), float("nan"), device="cuda")
