@@ -14,6 +14,29 @@
 
 namespace dcu {
 
+// Addressing of an H2 tensor in units of 16-byte pixels (8 fp16 channels): pixel (img, k-group kg, y, x) has its hi half at
+//   img * img + kg * plane + y * row + x      and its lo half `lo` pixels further.
+//   standard:  [n][hi|lo][C/8][H][W]          img = 2*(C/8)*H*W, plane = H*W, lo = (C/8)*H*W, row = W
+//   flat "F2": [hi|lo][C/8][plane_px]         img = period, plane = plane_px, lo = (C/8)*plane_px, row = stored row stride.
+// F2 keeps ALL images of a launch in one run of pixels per channel group (image k starts at pixel k*period), so that a
+// convolution can treat the whole batch as a 1-D signal (conv_tc2.cu, FLAT mode): RefineNet's small maps (22x22 ... 8x8)
+// then fill the 128-pixel MMA tiles instead of leaving most of a 16x8 tile empty.  Same-padded layers store their maps
+// with one zero gutter column and row (8x8 data in a 9x9 cell) that serves as the padding of every neighbour.
+struct H2Layout {
+  long long img, plane, lo;
+  int row;
+};
+__host__ __device__ inline H2Layout h2_standard(int c, int h, int w) {
+  H2Layout l;
+  l.plane = (long long)h * w; l.img = 2LL * (c >> 3) * l.plane; l.lo = (long long)(c >> 3) * l.plane; l.row = w;
+  return l;
+}
+__host__ __device__ inline H2Layout h2_flat(int c, int period, int row, long long plane_px) {
+  H2Layout l;
+  l.img = period; l.plane = plane_px; l.lo = (long long)(c >> 3) * plane_px; l.row = row;
+  return l;
+}
+
 // ---- one 3x3 convolution layer, device-side view ---------------------------------------------------
 struct ConvParams {
   const float* in;        // C4 [n][cin/4][hin][win][4]
@@ -40,6 +63,11 @@ struct ConvParams {
   int n_valid;            // real output channels (the weight block is zero-padded to NT rows)
   float wscale_inv;       // tcgen05 path: 2^-s, undoes the power-of-two weight scaling of the fp16 split (1.0 otherwise)
   unsigned long long* stats;   // optional [8] cycle counters for the tcgen05 kernel's roles (profiling), may be null
+  // tcgen05 pair kernel only.  out_layout.plane != 0: explicit addressing of the output tensor (after pool) instead of the
+  // standard one.  flat_in != 0: `in` is an F2 tensor with image period in_period and stored row stride in_row (hin x win
+  // are the data extents inside it); conv_tc2.cu FLAT mode.
+  H2Layout out_layout;
+  int flat_in, in_period, in_row;
 };
 
 // FFMA path: weights packed [cin/4][9 taps][4 cin][cout_total] with the cout axis permuted per 64-block
@@ -57,6 +85,7 @@ struct FirstConvParams {
   const float* lut;       // [256] fp32 (x-128)/255, host-computed (model_utils.py:46-50)
   float* out;             // C4 [n][16][hout][wout][4], or H2 [n][2][8][hout][wout][8] fp16 when out_h2 != 0
   int out_h2;
+  H2Layout out_layout;    // out_h2 only; plane == 0: the standard H2 tensor
   const float* w;         // [9][64]
   const float* bias; const float* alpha; const float* beta;   // [64]
   int n, hin, win, hout, wout, pad;
@@ -101,8 +130,11 @@ void launch_refine_finalize(const unsigned long long* keys, const int32_t* xy, i
 void launch_nchw_to_c4(const float* in, float* out, int n, int c, int h, int w, cudaStream_t s);
 void launch_c4_to_nchw(const float* in, float* out, int n, int c, int h, int w, cudaStream_t s);
 // sub: the NCHW input is [h*sub][w*sub] and pixel (y*sub, x*sub) is taken; rep: the NCHW output is [h*rep][w*rep] (nearest)
-void launch_nchw_to_h2(const float* in, void* out, int n, int c, int h, int w, cudaStream_t s, int sub = 1);
-void launch_h2_to_nchw(const void* in, float* out, int n, int c, int h, int w, cudaStream_t s, int rep = 1);
+// lay: addressing of the H2 side (nullptr: standard)
+void launch_nchw_to_h2(const float* in, void* out, int n, int c, int h, int w, cudaStream_t s, int sub = 1,
+                       const H2Layout* lay = nullptr);
+void launch_h2_to_nchw(const void* in, float* out, int n, int c, int h, int w, cudaStream_t s, int rep = 1,
+                       const H2Layout* lay = nullptr);
 
 // tcgen05 path (conv_tc.cu)
 struct TcLayerPack {
@@ -118,6 +150,7 @@ cudaError_t launch_conv3x3_tc(const ConvParams& p, const float* w_blocks, int n_
 int tc2_block_bytes(int nt);
 int tc2_stage_blocks(int up);       // weight blocks per bulk-copy stage (tensor-map box)
 // up != 0: p.in is the LOW-resolution tensor (hin x win) whose 2x nearest upsampling is the layer's input; hout = 2*hin
+int tc2_flat_rows(int in_row, int pad_or_up, int up);   // FLAT mode: rows of 16 pixels per halo box (tensor-map box height)
 cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const void* tmap_a, const void* tmap_w0, const void* tmap_w1,
                             int sm_count, cudaStream_t s);
 

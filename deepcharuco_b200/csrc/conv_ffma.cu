@@ -287,7 +287,8 @@ conv_first_kernel(FirstConvParams p, long long total_px) {
       }
     float4* outp = reinterpret_cast<float4*>(p.out);
     uint4* outh = reinterpret_cast<uint4*>(p.out);
-    const size_t plane = (size_t)p.hout * p.wout;
+    const H2Layout lay = p.out_layout.plane ? p.out_layout : h2_standard(64, p.hout, p.wout);
+    const size_t opix = (size_t)img * lay.img + (size_t)oy * lay.row + ox;
 #pragma unroll 2
     for (int g8 = 0; g8 < 8; ++g8) {          // 8 output channels per iteration
       float y[8];
@@ -310,9 +311,8 @@ conv_first_kernel(FirstConvParams p, long long total_px) {
         uint32_t h[4], l[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) split_h2(y[2 * e], y[2 * e + 1], h[e], l[e]);
-        const size_t pix = (size_t)oy * p.wout + ox;
-        outh[((size_t)img * 2 * 8 + g8) * plane + pix] = make_uint4(h[0], h[1], h[2], h[3]);
-        outh[((size_t)img * 2 * 8 + 8 + g8) * plane + pix] = make_uint4(l[0], l[1], l[2], l[3]);
+        outh[opix + (size_t)g8 * lay.plane] = make_uint4(h[0], h[1], h[2], h[3]);
+        outh[opix + (size_t)g8 * lay.plane + lay.lo] = make_uint4(l[0], l[1], l[2], l[3]);
       } else {
         outp[(((size_t)img * 16 + 2 * g8) * p.hout + oy) * p.wout + ox] = make_float4(y[0], y[1], y[2], y[3]);
         outp[(((size_t)img * 16 + 2 * g8 + 1) * p.hout + oy) * p.wout + ox] = make_float4(y[4], y[5], y[6], y[7]);
@@ -455,7 +455,7 @@ __global__ void c4_to_nchw_kernel(const float* in, float* out, int n, int c, int
     out[i] = in[((((size_t)img * (c >> 2) + (ch >> 2)) * h + y) * w + x) * 4 + (ch & 3)];
   }
 }
-__global__ void nchw_to_h2_kernel(const float* in, __half* out, int n, int c, int h, int w, int sub) {
+__global__ void nchw_to_h2_kernel(const float* in, __half* out, int n, int c, int h, int w, int sub, H2Layout lay) {
   const long long total = (long long)n * c * h * w;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % w); long long t = i / w;
@@ -464,33 +464,33 @@ __global__ void nchw_to_h2_kernel(const float* in, __half* out, int n, int c, in
     const float v = fminf(in[(((size_t)img * c + ch) * (h * sub) + (size_t)y * sub) * (w * sub) + (size_t)x * sub], 65504.f);
     const __half hi = __float2half_rn(v);
     const __half lo = __float2half_rn(v - __half2float(hi));
-    const size_t o = ((((size_t)img * 2) * (c >> 3) + (ch >> 3)) * h + y) * w + x;
+    const size_t o = (size_t)img * lay.img + (size_t)(ch >> 3) * lay.plane + (size_t)y * lay.row + x;
     out[o * 8 + (ch & 7)] = hi;
-    out[(o + (size_t)(c >> 3) * h * w) * 8 + (ch & 7)] = lo;
+    out[(o + (size_t)lay.lo) * 8 + (ch & 7)] = lo;
   }
 }
-__global__ void h2_to_nchw_kernel(const __half* in, float* out, int n, int c, int h, int w, int rep) {
+__global__ void h2_to_nchw_kernel(const __half* in, float* out, int n, int c, int h, int w, int rep, H2Layout lay) {
   const int ho = h * rep, wo = w * rep;
   const long long total = (long long)n * c * ho * wo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % wo) / rep; long long t = i / wo;
     const int y = (int)(t % ho) / rep; t /= ho;
     const int ch = (int)(t % c); const int img = (int)(t / c);
-    const size_t o = ((((size_t)img * 2) * (c >> 3) + (ch >> 3)) * h + y) * w + x;
-    out[i] = __half2float(in[o * 8 + (ch & 7)]) + __half2float(in[(o + (size_t)(c >> 3) * h * w) * 8 + (ch & 7)]);
+    const size_t o = (size_t)img * lay.img + (size_t)(ch >> 3) * lay.plane + (size_t)y * lay.row + x;
+    out[i] = __half2float(in[o * 8 + (ch & 7)]) + __half2float(in[(o + (size_t)lay.lo) * 8 + (ch & 7)]);
   }
 }
-void launch_nchw_to_h2(const float* in, void* out, int n, int c, int h, int w, cudaStream_t s, int sub) {
+void launch_nchw_to_h2(const float* in, void* out, int n, int c, int h, int w, cudaStream_t s, int sub, const H2Layout* lay) {
   const long long total = (long long)n * c * h * w;
   if (total <= 0) return;
   long long b = (total + 255) / 256; if (b > 148 * 16) b = 148 * 16;
-  nchw_to_h2_kernel<<<(int)b, 256, 0, s>>>(in, reinterpret_cast<__half*>(out), n, c, h, w, sub);
+  nchw_to_h2_kernel<<<(int)b, 256, 0, s>>>(in, reinterpret_cast<__half*>(out), n, c, h, w, sub, lay ? *lay : h2_standard(c, h, w));
 }
-void launch_h2_to_nchw(const void* in, float* out, int n, int c, int h, int w, cudaStream_t s, int rep) {
+void launch_h2_to_nchw(const void* in, float* out, int n, int c, int h, int w, cudaStream_t s, int rep, const H2Layout* lay) {
   const long long total = (long long)n * c * h * w * rep * rep;
   if (total <= 0) return;
   long long b = (total + 255) / 256; if (b > 148 * 16) b = 148 * 16;
-  h2_to_nchw_kernel<<<(int)b, 256, 0, s>>>(reinterpret_cast<const __half*>(in), out, n, c, h, w, rep);
+  h2_to_nchw_kernel<<<(int)b, 256, 0, s>>>(reinterpret_cast<const __half*>(in), out, n, c, h, w, rep, lay ? *lay : h2_standard(c, h, w));
 }
 
 void launch_nchw_to_c4(const float* in, float* out, int n, int c, int h, int w, cudaStream_t s) {

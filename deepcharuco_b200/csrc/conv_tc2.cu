@@ -19,6 +19,15 @@
 //   * "empty" / acc_full barriers are released by tcgen05.commit.cta_group::2 ... multicast::cluster with mask 0b11, i.e. they
 //     fire in both CTAs, so each CTA's producers and epilogue wait on their local copy;
 //   * acc_empty lives in the leader and counts the epilogue threads of BOTH CTAs (remote mbarrier.arrive via mapa).
+//
+// FLAT mode (ConvParams::flat_in, F2 tensors of common.cuh).  RefineNet's first maps are 22x22 ... 8x8 pixels: a 16x8 /
+// 16x16 pixel tile of such a map is mostly empty (8x8: 25 % of the MMA rows useful).  In FLAT mode all images of the launch
+// form ONE run of pixels j = k*period + y*row + x, an m-tile is 128 CONSECUTIVE pixels of that run and a tap (ky, kx) is the
+// same tile shifted by (ky-pad)*row + (kx-pad) pixels -- still nine descriptor start addresses into one halo buffer (core
+// matrix = 8 consecutive pixels, SBO = 128 B).  Valid convolutions compute and discard the wrap-around positions
+// (x >= wout or y >= hout); same-padded maps carry one zero gutter column / row that pads every neighbour (never written:
+// the epilogue only stores data positions).  Useful rows: 20x20 of 22x22 = 83 %, 18x18 of 20x20 = 81 %, 8x8 of 9x9 = 79 %.
+// The halo arrives as one 4-D TMA box {16 pixels, R rows of 16 pixels, 2 k-groups, hi|lo}.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -51,6 +60,11 @@ struct Tc2Cfg {
 struct Tc2Geo {
   int tr, tc, halo_w, halo_h, tiles_x, tiles_y, slices;
   long long tiles_per_slice, pairs_per_slice, total_pairs;
+  // A-operand addressing in 16-byte pixels: tap (ky, kx) of m-tile mt starts at a_org + ky*row_step + kx + mt_off;
+  // sbo = distance between consecutive groups of 8 M rows.  Standard: row_step = sbo = halo_w, a_org = 0.
+  int row_step, sbo, a_org;
+  int flat, tile_px, lead;     // FLAT: pixels per CTA tile (256; UP: 128), pixels loaded ahead of the tile start (multiple of 16)
+  H2Layout out;                // output addressing
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,6 +125,12 @@ __device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap*
   asm volatile(
       "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
@@ -196,13 +216,14 @@ __device__ __forceinline__ unsigned int orderable(float v) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-struct Tile2 { int img, slice, y0, x0; bool valid; };
+struct Tile2 { int img, slice, y0, x0; bool valid; };       // FLAT: x0 = first pixel of the CTA tile in the run, img / y0 unused
 __device__ __forceinline__ Tile2 decode_pair_tile(long long pt, uint32_t rank, const Tc2Geo& g) {
   Tile2 c;
   c.slice = (int)(pt / g.pairs_per_slice);
   long long t = (pt - (long long)c.slice * g.pairs_per_slice) * 2 + rank;
   c.valid = t < g.tiles_per_slice;
   if (!c.valid) t = g.tiles_per_slice - 1;            // odd tail: the peer recomputes the last tile and discards it
+  if (g.flat) { c.img = 0; c.y0 = 0; c.x0 = (int)(t * g.tile_px); return c; }
   const int tx = (int)(t % g.tiles_x); t /= g.tiles_x;
   const int ty = (int)(t % g.tiles_y);
   c.img = (int)(t / g.tiles_y);
@@ -271,8 +292,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       for (int q = 0; q < chunks; ++q) {
         mbar_wait<200>(&a_empty[st], ph ^ 1u);
         if (rank == 0) mbar_expect_tx(&a_full[st], 2u * (uint32_t)halo_px * 64u);
-        tma_load_5d_2sm(smem_u32(a_smem + (size_t)st * Cfg::A_STAGE_BYTES), &tmap_a, &a_full[st], (c.x0 - p.pad) * 8, c.y0 - p.pad,
-                        (p.cin_offset >> 3) + q * 2, 0, c.img);
+        if (g.flat)
+          tma_load_4d_2sm(smem_u32(a_smem + (size_t)st * Cfg::A_STAGE_BYTES), &tmap_a, &a_full[st], 0, (c.x0 - g.lead) >> 4,
+                          (p.cin_offset >> 3) + q * 2, 0);
+        else
+          tma_load_5d_2sm(smem_u32(a_smem + (size_t)st * Cfg::A_STAGE_BYTES), &tmap_a, &a_full[st], (c.x0 - p.pad) * 8, c.y0 - p.pad,
+                          (p.cin_offset >> 3) + q * 2, 0, c.img);
         if (++st == Cfg::A_STAGES) { st = 0; ph ^= 1u; }
       }
     }
@@ -297,7 +322,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     constexpr uint32_t IDESC_2N = IDESC_BASE | ((uint32_t)((2 * NT) >> 3) << 17);
     constexpr uint32_t IDESC_1N = IDESC_BASE | ((uint32_t)(NT >> 3) << 17);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint32_t a_desc_hi = (uint32_t)g.halo_w | (1u << 14);                 // SBO = halo_w * 16 B
+    const uint32_t a_desc_hi = (uint32_t)g.sbo | (1u << 14);                    // SBO = halo_w * 16 B (FLAT: 128 B)
     const uint32_t a_desc_lo0 = ((uint32_t)halo_px << 16);                      // LBO = plane
     constexpr uint32_t b_desc_hi = 8u | (1u << 14);                             // SBO = 128 B
     constexpr uint32_t bm_desc_lo0 = ((uint32_t)NT << 16);                      // main half: NT rows per k-group
@@ -307,7 +332,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       const int tri = mt / g.tc, tci = mt - tri * g.tc;
-      mt_off[mt] = (uint32_t)(tri * 16 * g.halo_w + tci * 8);
+      mt_off[mt] = g.flat ? (uint32_t)(mt * 128) : (uint32_t)(tri * 16 * g.halo_w + tci * 8);
     }
     int sa = 0, sb = 0, buf = 0; uint32_t pha = 0, phb = 0, phc = 0;
     for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
@@ -325,7 +350,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         for (int ky = 0; ky < ROWS; ++ky) {
           mbar_wait(&b_full[sb], phb);
           tc_fence_after();
-          const uint32_t a_row = a_hi + (uint32_t)((ky + (int)ph_a) * g.halo_w);
+          const uint32_t a_row = a_hi + (uint32_t)(g.a_org + (ky + (int)ph_a) * g.row_step);
           const uint32_t b_row = b_base0 + (uint32_t)sb * (Cfg::B_STAGE_BYTES >> 4);
           if (elect_one()) {
 #pragma unroll
@@ -372,14 +397,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int ch_base = (UP ? (c.slice >> 1) : c.slice) * NT;
 #pragma unroll 1
       for (int mt = grp; mt < MT; mt += 2) {
-        int oy, ox;
-        if (UP) {        // low-resolution pixel (y0 + prow, x0 + pcol), output phase (slice & 1, mt)
-          oy = 2 * (c.y0 + prow) + (c.slice & 1); ox = 2 * (c.x0 + pcol) + mt;
+        int oy, ox, img = c.img;
+        bool inb;
+        if (g.flat) {    // pixel j of the run -> (image, y, x) by the input's period / row stride; wrap-around positions are dropped
+          const int j = c.x0 + (UP ? 0 : mt * 128) + m;
+          img = j / p.in_period;
+          const int r = j - img * p.in_period;
+          const int y = r / p.in_row, x = r - y * p.in_row;
+          inb = c.valid && img < p.n && y < (UP ? p.hin : p.hout) && x < (UP ? p.win : p.wout);
+          oy = UP ? 2 * y + (c.slice & 1) : y; ox = UP ? 2 * x + mt : x;
         } else {
-          const int tri = mt / g.tc, tci = mt - tri * g.tc;
-          oy = c.y0 + tri * 16 + prow; ox = c.x0 + tci * 8 + pcol;
+          if (UP) {        // low-resolution pixel (y0 + prow, x0 + pcol), output phase (slice & 1, mt)
+            oy = 2 * (c.y0 + prow) + (c.slice & 1); ox = 2 * (c.x0 + pcol) + mt;
+          } else {
+            const int tri = mt / g.tc, tci = mt - tri * g.tc;
+            oy = c.y0 + tri * 16 + prow; ox = c.x0 + tci * 8 + pcol;
+          }
+          inb = c.valid && (oy < p.hout) && (ox < p.wout);
         }
-        const bool inb = c.valid && (oy < p.hout) && (ox < p.wout);
         float head_sum = 0.f;
 #pragma unroll 1
         for (int cc = 0; cc < NT / CW; ++cc) {
@@ -395,7 +430,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (p.logits != nullptr) {
             if (inb) {
               const size_t plane_o = (size_t)p.hout * p.wout;
-              float* o = p.logits + (size_t)c.img * p.n_valid * plane_o + (size_t)oy * p.wout + ox;
+              float* o = p.logits + (size_t)img * p.n_valid * plane_o + (size_t)oy * p.wout + ox;
 #pragma unroll
               for (int j = 0; j < CW; ++j)
                 if (ch0 + j < p.n_valid) o[(size_t)(ch0 + j) * plane_o] = v[j] + prm[ch0 + j];
@@ -423,15 +458,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
             const int hp = p.hout >> 1, wp = p.wout >> 1;
             if (c.valid && ((lane & 9) == 0) && (oy >> 1) < hp && (ox >> 1) < wp) {
-              const size_t plane_o = (size_t)hp * wp;
-              uint4* o = reinterpret_cast<uint4*>(p.out) + ((size_t)c.img * 2 * c8_out + (ch0 >> 3)) * plane_o + (size_t)(oy >> 1) * wp + (ox >> 1);
-              store_h2_16(o, (size_t)c8_out * plane_o, plane_o, v);
+              uint4* o = reinterpret_cast<uint4*>(p.out) + (size_t)img * g.out.img + (size_t)(ch0 >> 3) * g.out.plane +
+                         (size_t)(oy >> 1) * g.out.row + (ox >> 1);
+              store_h2_16(o, (size_t)g.out.lo, (size_t)g.out.plane, v);
             }
           } else if (p.ups) {
             if (inb) {
               const int hu = p.hout * 2, wu = p.wout * 2;
               const size_t plane_o = (size_t)hu * wu;
-              uint4* o = reinterpret_cast<uint4*>(p.out) + ((size_t)c.img * 2 * c8_out + (ch0 >> 3)) * plane_o + (size_t)(2 * oy) * wu + 2 * ox;
+              uint4* o = reinterpret_cast<uint4*>(p.out) + ((size_t)img * 2 * c8_out + (ch0 >> 3)) * plane_o + (size_t)(2 * oy) * wu + 2 * ox;
               const size_t lo_off = (size_t)c8_out * plane_o;
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
@@ -446,9 +481,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
           } else {
             if (inb) {
-              const size_t plane_o = (size_t)p.hout * p.wout;
-              uint4* o = reinterpret_cast<uint4*>(p.out) + ((size_t)c.img * 2 * c8_out + (ch0 >> 3)) * plane_o + (size_t)oy * p.wout + ox;
-              store_h2_16(o, (size_t)c8_out * plane_o, plane_o, v);
+              uint4* o = reinterpret_cast<uint4*>(p.out) + (size_t)img * g.out.img + (size_t)(ch0 >> 3) * g.out.plane +
+                         (size_t)oy * g.out.row + ox;
+              store_h2_16(o, (size_t)g.out.lo, (size_t)g.out.plane, v);
             }
           }
         }
@@ -457,7 +492,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           unsigned long long key = 0ull;
           if (inb) {
             const unsigned int idx = (unsigned)(oy * p.wout + ox);
-            if (p.heat != nullptr) p.heat[(size_t)c.img * p.hout * p.wout + idx] = s;
+            if (p.heat != nullptr) p.heat[(size_t)img * p.hout * p.wout + idx] = s;
             key = ((unsigned long long)orderable(s) << 32) | (unsigned long long)(~idx);
           }
 #pragma unroll
@@ -465,7 +500,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
             key = other > key ? other : key;
           }
-          if (lane == 0 && key != 0ull) atomicMax(p.head_key + c.img, key);
+          if (lane == 0 && key != 0ull) atomicMax(p.head_key + img, key);
         }
         tc_fence_before();
         mbar_arrive_cluster(&acc_empty[buf * MT + mt], 0);      // always the leader's barrier
@@ -493,10 +528,23 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  Tc2Geo g;
-  if (UP) {
+  Tc2Geo g{};
+  if (UP && (p.pad != 1 || p.pool || p.ups || p.hout != 2 * p.hin || p.wout != 2 * p.win)) return cudaErrorInvalidValue;
+  if (p.flat_in) {
+    // the batch as one run of pixels; CTA tile = 256 consecutive pixels (UP: 128, the two m-tiles are the column phases)
+    if (p.pool || p.ups || p.head_w || p.logits || p.in_period <= 0 || p.in_row <= 0) return cudaErrorInvalidValue;
+    if ((long long)p.n * p.in_period + 1024 > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const int back = (UP || p.pad) ? p.in_row + 1 : 0;            // pixels a tap reaches behind its output position
+    g.flat = 1; g.tile_px = UP ? 128 : 256;
+    g.lead = ceil_div(back, 16) * 16;
+    g.a_org = g.lead - back; g.row_step = p.in_row; g.sbo = 8;
+    g.tr = 1; g.tc = 1;
+    g.halo_w = 16; g.halo_h = tc2_flat_rows(p.in_row, (UP || p.pad) ? 1 : 0, UP ? 1 : 0);
+    g.tiles_x = 1; g.tiles_y = 1;
+    g.tiles_per_slice = ((long long)p.n * p.in_period + g.tile_px - 1) / g.tile_px;
+    if (UP) n_slices *= 2;
+  } else if (UP) {
     // tiles of 16 x 8 LOW-resolution pixels; the two m-tiles are the column phases; slices = channel slices x 2 row phases
-    if (p.pad != 1 || p.pool || p.ups || p.hout != 2 * p.hin || p.wout != 2 * p.win) return cudaErrorInvalidValue;
     g.tr = 1; g.tc = 1;
     g.halo_w = 10; g.halo_h = 18;
     g.tiles_x = ceil_div(p.win, 8); g.tiles_y = ceil_div(p.hin, 16);
@@ -506,9 +554,14 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
     g.halo_w = 8 * g.tc + 2; g.halo_h = 16 * g.tr + 2;
     g.tiles_x = ceil_div(p.wout, 8 * g.tc); g.tiles_y = ceil_div(p.hout, 16 * g.tr);
   }
+  if (!g.flat) {
+    g.row_step = g.halo_w; g.sbo = g.halo_w; g.a_org = 0;
+    g.tiles_per_slice = (long long)p.n * g.tiles_x * g.tiles_y;
+  }
   if (g.halo_w * g.halo_h > Cfg::MAX_HALO_PX) return cudaErrorInvalidValue;
+  g.out = p.out_layout.plane ? p.out_layout
+                             : (p.pool ? h2_standard(p.cout_total, p.hout >> 1, p.wout >> 1) : h2_standard(p.cout_total, p.hout, p.wout));
   g.slices = n_slices;
-  g.tiles_per_slice = (long long)p.n * g.tiles_x * g.tiles_y;
   g.pairs_per_slice = (g.tiles_per_slice + 1) / 2;
   g.total_pairs = g.pairs_per_slice * g.slices;
   if (g.total_pairs <= 0) return cudaSuccess;
@@ -520,6 +573,10 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
 }  // namespace
 
 int tc2_block_bytes(int nt) { return 48 * nt; }
+int tc2_flat_rows(int in_row, int pad_or_up, int up) {
+  const int back = pad_or_up ? in_row + 1 : 0, fwd = pad_or_up ? in_row + 1 : 2 * in_row + 2;
+  return ceil_div(ceil_div(back, 16) * 16 + (up ? 128 : 256) + fwd, 16);
+}
 int tc2_stage_blocks(int up) { return up ? 4 : 3; }
 
 cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const void* tmap_a, const void* tmap_w0, const void* tmap_w1,

@@ -297,6 +297,8 @@ struct DcuEngine {
   cudaEvent_t ev_start = nullptr, ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   bool overlap_first = true;
   bool fuse_up = true;          // RefineNet: fold the 2x nearest upsamplings into the consuming convolution (DCU_FUSE_UP=0: materialise)
+  bool flat = true;             // RefineNet maps up to conv4a's input as F2 runs (conv_tc2.cu FLAT mode; DCU_FLAT=0: per-patch tiles)
+  DevBuf flat8[3];              // 8x8 maps in 9x9 cells (conv2b / conv3a / conv3b outputs); gutters stay zero
   bool tc_pair = true;          // use the CTA-pair (cta_group::2) kernel for the 3x3 layers (DCU_TC_PAIR=0: single-CTA kernel)
   DevBuf stage2_in;             // conv2b output for mb2 frames (input of conv3a)
   DevBuf heads;                 // (Pa|Da) output for mb2 frames
@@ -331,7 +333,7 @@ struct DcuEngine {
     if (side) cudaStreamDestroy(side);
     if (ev_start) cudaEventDestroy(ev_start);
     for (int i = 0; i < 2; ++i) { if (ev_done[i]) cudaEventDestroy(ev_done[i]); if (ev_free[i]) cudaEventDestroy(ev_free[i]); }
-    DevBuf* all[] = {&bgr, &c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
+    DevBuf* all[] = {&flat8[0], &flat8[1], &flat8[2], &bgr, &c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
                      &ids, &counts, &offsets, &total, &kpts, &patches, &keys, &refined, &scan_state, &frames};
     for (DevBuf* b : all) b->release();
     FirstLayer* fl[] = {&det_first, &ref_first};
@@ -451,6 +453,26 @@ static int make_tmap(CUtensorMap* tm, const void* base, int n, int cin, int h, i
   return DCU_OK;
 }
 
+// F2 tensor (common.cuh) as a 4-D tensor map {16 pixels x 8 halves, rows of 16 pixels, C/8, hi|lo}; box = {128, box_rows, 2, 2}.
+// `rows` bounds the pixels that hold data (reads beyond are zero-filled); plane_px is the allocated run length per channel group.
+static int make_tmap_flat(CUtensorMap* tm, const void* base, long long px_used, int cin, long long plane_px, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (plane_px % 16 != 0 || px_used > plane_px) return fail(DCU_ERR_INVALID, "flat tensor map: bad plane size");
+  cuuint64_t dims[4] = {128, (cuuint64_t)((px_used + 15) / 16), (cuuint64_t)(cin / 8), 2};
+  cuuint64_t strides[3] = {256, (cuuint64_t)plane_px * 16, (cuuint64_t)plane_px * 16 * (cin / 8)};
+  cuuint32_t box[4] = {128, (cuuint32_t)box_rows, 2, 2};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DCU_ERR_CUDA, "cuTensorMapEncodeTiled (flat) failed: " + std::to_string((int)r));
+  return DCU_OK;
+}
+
+struct FlatIn { int period, row; long long plane_px; };    // the layer's input is an F2 tensor (conv_tc2.cu FLAT mode)
+static long long flat_plane_px(int n, int period) { return (((long long)n * period + 15) / 16) * 16; }
+
 struct HeadFuse { const float* w = nullptr; float b = 0.f; unsigned long long* keys = nullptr; float* heat = nullptr; };
 static unsigned long long* g_tc_stats = nullptr;   // device [8]; set by dcu_debug_tc_stats (profiling only)
 
@@ -458,8 +480,10 @@ static unsigned long long* g_tc_stats = nullptr;   // device [8]; set by dcu_deb
 // producer (l.ups) and its consumer (l.ups_in) is not materialised -- the producer stores its low-resolution output and the
 // consumer runs the phase-collapsed 2x2 kernels on it (`in` is then the hin/2 x win/2 tensor).
 static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, float* out, int n, int hin, int win,
-                   const HeadFuse* hf, cudaStream_t s, bool fuse_up = false) {
+                   const HeadFuse* hf, cudaStream_t s, bool fuse_up = false, const FlatIn* fin = nullptr,
+                   const H2Layout* lout = nullptr) {
   const bool up_in = fuse_up && l.ups_in;
+  if ((fin || lout) && !(impl == DCU_CONV_TCGEN05 && e->tc_pair)) return fail(DCU_ERR_INVALID, "flat layouts need the CTA-pair kernel");
   ConvParams p{};
   p.in = in; p.out = out; p.bias = l.bias.as<float>(); p.alpha = l.alpha.as<float>(); p.beta = l.beta.as<float>();
   p.n = n; p.cin = l.cin; p.cout_total = l.cout; p.hin = up_in ? hin / 2 : hin; p.win = up_in ? win / 2 : win;
@@ -468,14 +492,18 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
   p.stats = g_tc_stats;
   p.wscale_inv = (impl == DCU_CONV_TCGEN05) ? 1.0f / (up_in ? l.up_scale : l.tc_scale) : 1.0f;
   p.ksize = 3;
+  if (fin) { p.flat_in = 1; p.in_period = fin->period; p.in_row = fin->row; }
+  if (lout) p.out_layout = *lout;
   if (n <= 0) return DCU_OK;
   e->prof_begin(0, 2.0 * 9.0 * l.cin * l.cout * (double)p.hout * p.wout * n, s, l.cin, l.cout, p.hout, p.wout, n);
   if (impl == DCU_CONV_TCGEN05) {
     if (l.tc_nt == 0) return fail(DCU_ERR_UNSUPPORTED, "layer shape not supported by the tcgen05 kernel");
     const TcGeom g = tc_geom(l.tc_nt, p.hout, p.wout);
     CUtensorMap tm;
-    int rc = up_in ? make_tmap(&tm, in, n, l.cin, p.hin, p.win, 10, 18)
-                   : make_tmap(&tm, in, n, l.cin, hin, win, 8 * g.tc + 2, 16 * g.tr + 2);
+    int rc = fin ? make_tmap_flat(&tm, in, (long long)n * fin->period, l.cin, fin->plane_px,
+                                  tc2_flat_rows(fin->row, (up_in || l.pad) ? 1 : 0, up_in ? 1 : 0))
+             : up_in ? make_tmap(&tm, in, n, l.cin, p.hin, p.win, 10, 18)
+                     : make_tmap(&tm, in, n, l.cin, hin, win, 8 * g.tc + 2, 16 * g.tr + 2);
     if (rc) return rc;
     if (fuse_up && !e->tc_pair) return fail(DCU_ERR_INVALID, "upsample fusion needs the CTA-pair kernel");
     cudaError_t ce = e->tc_pair
@@ -493,9 +521,10 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
 }
 
 static int run_first(DcuEngine* e, const FirstLayer& f, const uint8_t* in_u8, const float* in_f32, float* out, int n,
-                     int hin, int win, int out_h2, cudaStream_t s) {
+                     int hin, int win, int out_h2, cudaStream_t s, const H2Layout* lout = nullptr) {
   FirstConvParams p{};
   p.out_h2 = out_h2;
+  if (lout) p.out_layout = *lout;
   p.in_u8 = in_u8; p.in_f32 = in_f32; p.lut = e->lut.as<float>(); p.out = out; p.w = f.w.as<float>();
   p.bias = f.bias.as<float>(); p.alpha = f.alpha.as<float>(); p.beta = f.beta.as<float>();
   p.n = n; p.hin = hin; p.win = win; p.pad = f.pad; p.hout = hin + 2 * f.pad - 2; p.wout = win + 2 * f.pad - 2;
@@ -619,17 +648,33 @@ static int refine_run(DcuEngine* e, const float* patches, const int32_t* xy, int
     const int m = std::min(e->rp, p - p0);
     unsigned long long* keys = e->keys.as<unsigned long long>() + p0;
     CK(cudaMemsetAsync(keys, 0, (size_t)m * sizeof(unsigned long long), s));
+    // tcgen05 pair kernel: the three 2x upsamplings are never materialised (run_3x3: fuse_up)
+    const bool fu = e->fuse_up && e->tc_pair && e->conv_impl == DCU_CONV_TCGEN05 && e->ref[5].ups_in && e->ref[7].ups_in &&
+                    e->ref[9].ups_in;
+    if (fu && e->flat && e->flat8[0].p) {
+      // small maps as F2 runs (conv_tc2.cu FLAT mode): 22x22 and 20x20 dense, 8x8 in 9x9 cells with zero gutters (flat8[],
+      // zeroed once at creation; only data positions are ever written)
+      const long long pl22 = flat_plane_px(m, 484), pl20 = flat_plane_px(m, 400), pl9 = flat_plane_px(e->rp, 81);
+      const H2Layout l22 = h2_flat(64, 484, 22, pl22), l20 = h2_flat(64, 400, 20, pl20), l9 = h2_flat(128, 81, 9, pl9);
+      const FlatIn f22{484, 22, pl22}, f20{400, 20, pl20}, f9{81, 9, pl9};
+      float* g0 = e->flat8[0].as<float>(); float* g1 = e->flat8[1].as<float>(); float* g2 = e->flat8[2].as<float>();
+      if ((rc = run_first(e, e->ref_first, nullptr, patches + (size_t)p0 * 576, a0, m, 24, 24, 1, s, &l22))) return rc;  // conv1a -> 22
+      if ((rc = run_3x3(e, e->ref[0], e->conv_impl, a0, a1, m, 22, 22, nullptr, s, false, &f22, &l20))) return rc;     // conv1b -> 20
+      if ((rc = run_3x3(e, e->ref[1], e->conv_impl, a1, a0, m, 20, 20, nullptr, s, false, &f20, nullptr))) return rc;  // conv2a -> 18
+      if ((rc = run_3x3(e, e->ref[2], e->conv_impl, a0, g0, m, 18, 18, nullptr, s, false, nullptr, &l9))) return rc;   // conv2b -> 16 -> pool 8
+      if ((rc = run_3x3(e, e->ref[3], e->conv_impl, g0, g1, m, 8, 8, nullptr, s, false, &f9, &l9))) return rc;         // conv3a
+      if ((rc = run_3x3(e, e->ref[4], e->conv_impl, g1, g2, m, 8, 8, nullptr, s, true, &f9, &l9))) return rc;          // conv3b (-> up 16)
+      if ((rc = run_3x3(e, e->ref[5], e->conv_impl, g2, a0, m, 16, 16, nullptr, s, true, &f9, nullptr))) return rc;    // conv4a
+    } else {
     if ((rc = run_first(e, e->ref_first, nullptr, patches + (size_t)p0 * 576, a0, m, 24, 24, e->conv_impl == DCU_CONV_TCGEN05, s)))
       return rc;                                                                                  // conv1a -> 22
     if ((rc = run_3x3(e, e->ref[0], e->conv_impl, a0, a1, m, 22, 22, nullptr, s))) return rc;   // conv1b -> 20
     if ((rc = run_3x3(e, e->ref[1], e->conv_impl, a1, a0, m, 20, 20, nullptr, s))) return rc;   // conv2a -> 18
     if ((rc = run_3x3(e, e->ref[2], e->conv_impl, a0, a1, m, 18, 18, nullptr, s))) return rc;   // conv2b -> 16 -> pool 8
-    // tcgen05 pair kernel: the three 2x upsamplings are never materialised (run_3x3: fuse_up)
-    const bool fu = e->fuse_up && e->tc_pair && e->conv_impl == DCU_CONV_TCGEN05 && e->ref[5].ups_in && e->ref[7].ups_in &&
-                    e->ref[9].ups_in;
     if ((rc = run_3x3(e, e->ref[3], e->conv_impl, a1, a0, m, 8, 8, nullptr, s))) return rc;         // conv3a
     if ((rc = run_3x3(e, e->ref[4], e->conv_impl, a0, a1, m, 8, 8, nullptr, s, fu))) return rc;     // conv3b -> up 16
     if ((rc = run_3x3(e, e->ref[5], e->conv_impl, a1, a0, m, 16, 16, nullptr, s, fu))) return rc;   // conv4a
+    }
     if ((rc = run_3x3(e, e->ref[6], e->conv_impl, a0, a1, m, 16, 16, nullptr, s, fu))) return rc;   // conv4b -> up 32
     if ((rc = run_3x3(e, e->ref[7], e->conv_impl, a1, a0, m, 32, 32, nullptr, s, fu))) return rc;   // conv5a
     if ((rc = run_3x3(e, e->ref[8], e->conv_impl, a0, a1, m, 32, 32, nullptr, s, fu))) return rc;   // conv5b -> up 64
@@ -758,6 +803,12 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   if (const char* v = getenv("DCU_OVERLAP_FIRST")) e->overlap_first = atoi(v) != 0;
   if (const char* v = getenv("DCU_TC_PAIR")) e->tc_pair = atoi(v) != 0;
   if (const char* v = getenv("DCU_FUSE_UP")) e->fuse_up = atoi(v) != 0;
+  if (const char* v = getenv("DCU_FLAT")) e->flat = atoi(v) != 0;
+  if (e->has_ref && e->flat)
+    for (int i = 0; i < 3; ++i) {
+      TRYC(e->flat8[i].alloc((size_t)flat_plane_px(e->rp, 81) * 16 * 2 * 16));     // [hi|lo][128/8][plane px] x 16 B
+      TRYC(cudaMemset(e->flat8[i].p, 0, e->flat8[i].bytes));
+    }
   TRYC(e->act[0].alloc(act_floats * 4));
   TRYC(e->act[1].alloc(act_floats * 4));
   TRYC(e->stage2_in.alloc((size_t)e->mb2 * 64 * (H / 4) * (W / 4) * 4));
@@ -1092,16 +1143,41 @@ int dcu_debug_conv_layer(DcuEngine* e, int net, int layer, int conv_impl, const 
   const bool h2 = !fl && conv_impl == DCU_CONV_TCGEN05;     // the tcgen05 kernel reads and writes the H2 layout
   // upsample fusion (run_3x3): the consumer takes the low-resolution tensor, the producer stores one
   const bool fu = h2 && e->fuse_up && e->tc_pair && (l->ups_in || l->ups);
+  // RefineNet layers 1..6 in the F2 layouts refine_run uses (same rule: pair kernel + upsample fusion + DCU_FLAT)
+  const bool flat = h2 && net == 1 && layer >= 1 && layer <= 6 && e->flat && e->fuse_up && e->tc_pair && e->ref[5].ups_in;
+  const bool flat_in = flat && layer != 3, flat_out = flat && layer != 2 && layer != 6;
+  FlatIn fin{}; H2Layout lin{}, lout{};
+  if (flat_in) {
+    const int hi = (layer == 6) ? h / 2 : h, wi = (layer == 6) ? w / 2 : w, g = (layer >= 4) ? 1 : 0;   // g: zero gutter column / row
+    fin.period = (hi + g) * (wi + g); fin.row = wi + g; fin.plane_px = flat_plane_px(n, fin.period);
+    lin = h2_flat(cin, fin.period, fin.row, fin.plane_px);
+    tin.release();
+    CK(tin.alloc((size_t)fin.plane_px * 16 * 2 * (cin / 8)));
+    CK(cudaMemsetAsync(tin.p, 0, tin.bytes, s));
+  }
+  if (flat_out) {
+    const int hs = (layer == 5) ? ho : hf, ws = (layer == 5) ? wo : wf, g = (layer >= 3) ? 1 : 0;
+    const int period = (hs + g) * (ws + g);
+    const long long pl = flat_plane_px(n, period);
+    lout = h2_flat(cout, period, ws + g, pl);
+    tout.release();
+    CK(tout.alloc((size_t)pl * 16 * 2 * (cout / 8)));
+    CK(cudaMemsetAsync(tout.p, 0, tout.bytes, s));
+  }
   if (fl) {
     rc = run_first(e, *fl, nullptr, in_dev, tout.as<float>(), n, h, w, 0, s);
   } else {
-    if (h2 && fu && l->ups_in) launch_nchw_to_h2(in_dev, tin.p, n, cin, h / 2, w / 2, s, 2);
+    if (flat_in) launch_nchw_to_h2(in_dev, tin.p, n, cin, layer == 6 ? h / 2 : h, layer == 6 ? w / 2 : w, s, layer == 6 ? 2 : 1, &lin);
+    else if (h2 && fu && l->ups_in) launch_nchw_to_h2(in_dev, tin.p, n, cin, h / 2, w / 2, s, 2);
     else if (h2) launch_nchw_to_h2(in_dev, tin.p, n, cin, h, w, s);
     else launch_nchw_to_c4(in_dev, tin.as<float>(), n, cin, h, w, s);
-    rc = run_3x3(e, *l, conv_impl, tin.as<float>(), tout.as<float>(), n, h, w, nullptr, s, fu);
+    rc = run_3x3(e, *l, conv_impl, tin.as<float>(), tout.as<float>(), n, h, w, nullptr, s, fu, flat_in ? &fin : nullptr,
+                 flat_out ? &lout : nullptr);
   }
   if (rc == DCU_OK) {
-    if (h2 && fu && l->ups) launch_h2_to_nchw(tout.p, out_dev, n, cout, ho, wo, s, 2);
+    if (flat_out && layer == 5) launch_h2_to_nchw(tout.p, out_dev, n, cout, ho, wo, s, 2, &lout);
+    else if (flat_out) launch_h2_to_nchw(tout.p, out_dev, n, cout, hf, wf, s, 1, &lout);
+    else if (h2 && fu && l->ups) launch_h2_to_nchw(tout.p, out_dev, n, cout, ho, wo, s, 2);
     else if (h2) launch_h2_to_nchw(tout.p, out_dev, n, cout, hf, wf, s);
     else launch_c4_to_nchw(tout.as<float>(), out_dev, n, cout, hf, wf, s);
     cudaError_t ce = cudaStreamSynchronize(s);

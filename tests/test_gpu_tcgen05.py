@@ -39,11 +39,12 @@ SHAPES = [  # net, layer, cin, h, w, cout, out_h, out_w
 UPSAMPLED_INPUT = {(1, 6), (1, 8), (1, 10)}
 
 
-@pytest.mark.parametrize("shape", SHAPES)
-def test_layer_tcgen05_matches_fp32_kernel(engine, shape):
+# n = 37 patches: RefineNet's small maps run as one flat run of pixels (conv_tc2.cu FLAT mode), so images straddle tile and
+# CTA-pair boundaries and the last pair is ragged
+@pytest.mark.parametrize("shape,n", [(s, 3) for s in SHAPES] + [(s, 37) for s in SHAPES if s[0] == 1 and s[1] <= 6])
+def test_layer_tcgen05_matches_fp32_kernel(engine, shape, n):
     net, layer, cin, h, w, cout, oh, ow = shape
-    rng = np.random.default_rng(layer * 7 + net)
-    n = 3
+    rng = np.random.default_rng(layer * 7 + net + n)
     if (net, layer) in UPSAMPLED_INPUT:
         x = np.maximum(rng.standard_normal((n, cin, h // 2, w // 2)).astype(np.float32), 0).repeat(2, axis=2).repeat(2, axis=3)
         x = torch.from_numpy(np.ascontiguousarray(x)).cuda()
