@@ -144,8 +144,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step (BASELINE config 3: 256)")
     ap.add_argument("--conv", default=os.environ.get("DCU_CONV_IMPL", ""), help="ffma | tcgen05 (default: library default)")
@@ -238,12 +238,14 @@ def main():
     for i in range(2):
         step_device(i)
     conv_ms, conv_flops, conv_n = eng.profile_read(0)
+    conv_issued = eng.profile_read_issued(0)
     dec_ms, dec_bytes, dec_n = eng.profile_read(3)
     first_ms, _, _ = eng.profile_read(1)
     heads_ms, _, _ = eng.profile_read(2)
     eng.profile_enable(False)
     peaks = read_peaks()
     achieved_tf = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    issued_tf = conv_issued / (conv_ms / 1e3) / 1e12 if (conv_ms > 0 and conv_issued > 0) else None
     peak_tf = peaks["bf16_sustained"]
     step_ms_prof = conv_ms + dec_ms + first_ms + heads_ms
     dec_bytes += 2 * (total_k * (2304 + 2304 + 16))          # + K*(patch read + patch write + record), 2 profiled steps
@@ -271,13 +273,14 @@ def main():
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      ms_per_step=ms_e2e / args.steps, api="dcu_infer_batch_host (pinned host u8 frames in, packed keypoints out)"),
             gpu_launches=int(launches),
-            roofline=dict(bound="tensor", kernel="conv3x3_tc_kernel (all 3x3 layer shapes of both networks, aggregated over launches)",
+            roofline=dict(bound="tensor", kernel="conv_tc2_kernel (CTA-pair tcgen05 3x3 convolution; all 3x3 layer shapes of both networks, aggregated over launches)",
                           achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf if peak_tf else None,
                           peak_source=f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
-                          note="achieved = ALGORITHMIC flops (2*MAC of the fp32 convolutions, SURVEY.md 8d).  The parity-safe fp16 hi/lo "
-                               "split issues 3 tensor-core products per MAC, so the tensor pipes run at issued = 3 x achieved.",
-                          issued_tflops=3.0 * achieved_tf if eng.conv_impl == Nn.CONV_TCGEN05 else None,
-                          issued_frac=(3.0 * achieved_tf / peak_tf) if (peak_tf and eng.conv_impl == Nn.CONV_TCGEN05) else None,
+                          note="achieved = ALGORITHMIC flops (2*MAC of the reference's fp32 convolutions, SURVEY.md 8d).  The parity-safe "
+                               "fp16 hi/lo split issues 3 tensor-core products per MAC (ceiling: frac 1/3); upsample-fused layers issue 4 of 9 "
+                               "taps.  issued_tflops = what the tensor pipes execute (all MMAs, padded tile rows included).",
+                          issued_tflops=issued_tf,
+                          issued_frac=(issued_tf / peak_tf) if (peak_tf and issued_tf) else None,
                           traffic=conv_traffic, traffic_source=traffic_src, launches=int(conv_n), kernel_ms_per_step=conv_ms / 2,
                           share_of_step=conv_ms / step_ms_prof if step_ms_prof else None,
                           decode_gather=dict(bound="hbm", achieved=(dec_bytes / (dec_ms / 1e3) / 1e9) if dec_ms > 0 else 0.0,

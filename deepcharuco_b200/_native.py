@@ -19,7 +19,7 @@ CONV_DEFAULT = CONV_TCGEN05   # tcgen05 tensor-core path (fp16 hi/lo split); CON
 EXPORTS = [
     "dcu_create", "dcu_destroy", "dcu_detector_forward", "dcu_detector_forward_f32", "dcu_extract_patches",
     "dcu_decode_gather", "dcu_refine_forward", "dcu_infer_batch", "dcu_infer_batch_host", "dcu_infer_batch_host_bgr", "dcu_bgr_to_gray",
-    "dcu_debug_conv_layer", "dcu_debug_tc_stats", "dcu_set_conv_impl", "dcu_launch_count", "dcu_profile_enable", "dcu_profile_read", "dcu_profile_records", "dcu_detector_flops_per_frame",
+    "dcu_debug_conv_layer", "dcu_debug_tc_stats", "dcu_set_conv_impl", "dcu_launch_count", "dcu_profile_enable", "dcu_profile_read", "dcu_profile_read_issued", "dcu_profile_records", "dcu_detector_flops_per_frame",
     "dcu_refine_flops_per_patch", "dcu_last_error", "dcu_version",
 ]
 
@@ -74,6 +74,7 @@ def lib():
     L.dcu_set_conv_impl.argtypes = [vp, i32]
     L.dcu_profile_enable.argtypes = [vp, i32]
     L.dcu_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
+    L.dcu_profile_read_issued.argtypes = [vp, i32, C.POINTER(C.c_double)]
     L.dcu_profile_records.argtypes = [vp, i32, vp, C.POINTER(i32)]
     L.dcu_launch_count.argtypes = [vp]
     L.dcu_launch_count.restype = i64
@@ -198,6 +199,11 @@ class Engine:
         ms, work, n = C.c_double(0), C.c_double(0), C.c_int64(0)
         check(lib().dcu_profile_read(self._h, int(cls), C.byref(ms), C.byref(work), C.byref(n)))
         return ms.value, work.value, n.value
+
+    def profile_read_issued(self, cls=0):
+        w = C.c_double(0)
+        check(lib().dcu_profile_read_issued(self._h, int(cls), C.byref(w)))
+        return w.value
 
     def profile_records(self, cap=4096):
         """Per-launch records since profile_enable: float64 [n][8] = cls, ms, work, cin, cout, hout, wout, n."""

@@ -68,7 +68,9 @@ struct ConvParams {
   // are the data extents inside it); conv_tc2.cu FLAT mode.
   H2Layout out_layout;
   int flat_in, in_period, in_row;
+  const struct TcBn* host_bn;   // host copy of bias / alpha / beta: the pair kernel takes them by value (constant bank)
 };
+struct TcBn { float v[3][512]; };   // [bias | alpha | beta][channel]
 
 // FFMA path: weights packed [cin/4][9 taps][4 cin][cout_total] with the cout axis permuted per 64-block
 // so a thread's 8 channels are two float4 that are bank-conflict free (see conv_ffma.cu).
@@ -151,8 +153,9 @@ int tc2_block_bytes(int nt);
 int tc2_stage_blocks(int up);       // weight blocks per bulk-copy stage (tensor-map box)
 // up != 0: p.in is the LOW-resolution tensor (hin x win) whose 2x nearest upsampling is the layer's input; hout = 2*hin
 int tc2_flat_rows(int in_row, int pad_or_up, int up);   // FLAT mode: rows of 16 pixels per halo box (tensor-map box height)
+// issued_flops (optional): 2 x the MACs the tensor pipes execute for this launch (3 products, padded tiles included)
 cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const void* tmap_a, const void* tmap_w0, const void* tmap_w1,
-                            int sm_count, cudaStream_t s);
+                            int sm_count, cudaStream_t s, double* issued_flops = nullptr);
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

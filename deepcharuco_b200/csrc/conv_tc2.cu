@@ -31,6 +31,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dcu {
@@ -39,22 +41,24 @@ namespace {
 
 constexpr int T2_THREADS = 384;
 
-template <int NT, bool UP = false>
+// WRES (weights resident): a 64 -> 64 layer's whole weight set (4 chunks x 3 kernel rows = 12 stages, 110.6 kB per rank) stays in
+// shared memory for the lifetime of the CTA instead of being re-fetched for every tile.  The kernel is bound by the shared-memory
+// data pipe (tensor-core operand fetches + fills, profiles/r1_ncu_conv_tc2.txt: 77 % + 23 %); the weight refills were 10 % of it.
+template <int NT, bool UP = false, bool WRES = false>
 struct Tc2Cfg {
   static constexpr int MT = 2;
   static constexpr int STAGE_BLOCKS = UP ? 4 : 3;                  // weight blocks per stage (one kernel row; UP: 2 taps x 2 column phases)
   static constexpr int NBUF = 512 / (MT * 2 * NT);
   static constexpr int A_STAGES = 4;
-  static constexpr int B_STAGES = (NT == 64) ? 6 : 4;
+  static constexpr int B_STAGES = WRES ? 12 : ((NT == 64) ? 6 : 4);
   static constexpr int MAX_HALO_PX = 34 * 10;
   static constexpr int A_STAGE_BYTES = 4 * MAX_HALO_PX * 16;
   static constexpr int B_MAIN_BYTES = 2 * NT * 16;                 // 2 k-groups x NT rows x 8 fp16 (this rank's half of [w_hi | w_lo])
   static constexpr int B_X_BYTES = 2 * (NT / 2) * 16;              // 2 k-groups x NT/2 rows     (this rank's half of w_hi)
   static constexpr int B_BLOCK_BYTES = B_MAIN_BYTES + B_X_BYTES;   // 48 * NT
   static constexpr int B_STAGE_BYTES = STAGE_BLOCKS * B_BLOCK_BYTES;
-  static constexpr int PARAM_BYTES = 3 * 512 * 4;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + PARAM_BYTES + BAR_BYTES + 1024;
+  static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + BAR_BYTES + 1024;
 };
 
 struct Tc2Geo {
@@ -232,11 +236,13 @@ __device__ __forceinline__ Tile2 decode_pair_tile(long long pt, uint32_t rank, c
   return c;
 }
 
-template <int NT, int KS, bool UP>
+template <int NT, int KS, bool UP, bool WRES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w0,
-                const __grid_constant__ CUtensorMap tmap_w1, const ConvParams p, const Tc2Geo g) {
-  using Cfg = Tc2Cfg<NT, UP>;
+                const __grid_constant__ CUtensorMap tmap_w1, const ConvParams p, const Tc2Geo g, const __grid_constant__ TcBn bn) {
+  // bn: bias / BN scale / BN shift by value = constant bank.  The epilogue's channel index is warp-uniform, so these become
+  // uniform constant loads instead of shared-memory reads (the shared-memory data pipe is what bounds this kernel).
+  using Cfg = Tc2Cfg<NT, UP, WRES>;
   constexpr int MT = Cfg::MT, NBUF = Cfg::NBUF, B_STAGES = Cfg::B_STAGES;
   // UP (input = 2x nearest upsampling of the tensor in HBM): per output phase (a, b) the 3x3 taps collapse to 2x2 taps on
   // the low-resolution tensor, so a weight stage is one of 2 kernel rows = 2 taps x 2 column phases (see header).
@@ -245,8 +251,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* a_smem = smem_raw;
   uint8_t* b_smem = a_smem + Cfg::A_STAGES * Cfg::A_STAGE_BYTES;
-  float* prm = reinterpret_cast<float*>(b_smem + B_STAGES * Cfg::B_STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(prm) + Cfg::PARAM_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + B_STAGES * Cfg::B_STAGE_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + Cfg::A_STAGES;
   uint64_t* b_full = a_empty + Cfg::A_STAGES;
@@ -262,11 +267,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int chunks = p.cin >> 4;
   const int halo_px = g.halo_w * g.halo_h;
 
-  for (int i = threadIdx.x; i < p.cout_total; i += T2_THREADS) {
-    prm[i] = p.bias[i];
-    prm[512 + i] = p.alpha[i];
-    prm[1024 + i] = p.beta[i];
-  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
@@ -307,6 +307,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(wm)) : "memory");
     int st = 0; uint32_t ph = 0;
     for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
+      if (WRES && pt != cluster_id) break;              // resident weights (one slice): loaded with the first tile only
       const int slice = (int)(pt / g.pairs_per_slice);
       const int blk0 = slice * chunks * TAPS;
       for (int blk = 0; blk < chunks * TAPS; blk += SB) {
@@ -348,8 +349,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
 #pragma unroll 1
         for (int ky = 0; ky < ROWS; ++ky) {
-          mbar_wait(&b_full[sb], phb);
-          tc_fence_after();
+          if (!WRES || pt == cluster_id) {
+            mbar_wait(&b_full[sb], phb);
+            tc_fence_after();
+          }
           const uint32_t a_row = a_hi + (uint32_t)(g.a_org + (ky + (int)ph_a) * g.row_step);
           const uint32_t b_row = b_base0 + (uint32_t)sb * (Cfg::B_STAGE_BYTES >> 4);
           if (elect_one()) {
@@ -368,7 +371,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 umma2_f16_w(d + NT, da_lo, a_desc_hi, b_x, b_desc_hi, IDESC_1N, 1u);                        // + a_lo*w_hi
               }
             }
-            umma2_commit_mc(&b_empty[sb]);
+            if (!WRES) umma2_commit_mc(&b_empty[sb]);
             if (ky == ROWS - 1) umma2_commit_mc(&a_empty[sa]);
             if (ky == ROWS - 1 && q == chunks - 1) umma2_commit_mc(&acc_full[buf]);
           }
@@ -433,15 +436,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               float* o = p.logits + (size_t)img * p.n_valid * plane_o + (size_t)oy * p.wout + ox;
 #pragma unroll
               for (int j = 0; j < CW; ++j)
-                if (ch0 + j < p.n_valid) o[(size_t)(ch0 + j) * plane_o] = v[j] + prm[ch0 + j];
+                if (ch0 + j < p.n_valid) o[(size_t)(ch0 + j) * plane_o] = v[j] + bn.v[0][ch0 + j];
             }
             continue;
           }
 #pragma unroll
           for (int j = 0; j < CW; j += 4) {
-            const float4 bi = *reinterpret_cast<const float4*>(&prm[ch0 + j]);
-            const float4 al = *reinterpret_cast<const float4*>(&prm[512 + ch0 + j]);
-            const float4 be = *reinterpret_cast<const float4*>(&prm[1024 + ch0 + j]);
+            const float4 bi = *reinterpret_cast<const float4*>(&bn.v[0][ch0 + j]);
+            const float4 al = *reinterpret_cast<const float4*>(&bn.v[1][ch0 + j]);
+            const float4 be = *reinterpret_cast<const float4*>(&bn.v[2][ch0 + j]);
             v[j + 0] = fmaxf(fmaf(v[j + 0] + bi.x, al.x, be.x), 0.0f);
             v[j + 1] = fmaxf(fmaf(v[j + 1] + bi.y, al.y, be.y), 0.0f);
             v[j + 2] = fmaxf(fmaf(v[j + 2] + bi.z, al.z, be.z), 0.0f);
@@ -518,13 +521,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
-template <int NT, int KS, bool UP>
+template <int NT, int KS, bool UP, bool WRES = false>
 cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta, const CUtensorMap* w0, const CUtensorMap* w1,
-                        int sm_count, cudaStream_t s) {
-  using Cfg = Tc2Cfg<NT, UP>;
+                        int sm_count, cudaStream_t s, double* issued_flops) {
+  using Cfg = Tc2Cfg<NT, UP, WRES>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NT, KS, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NT, KS, UP, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
@@ -565,8 +568,11 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
   g.pairs_per_slice = (g.tiles_per_slice + 1) / 2;
   g.total_pairs = g.pairs_per_slice * g.slices;
   if (g.total_pairs <= 0) return cudaSuccess;
+  // per pair work item and (16-channel chunk, tap, m-tile): one M=256 x N=2*NT x K=16 and one M=256 x N=NT x K=16 MMA
+  if (issued_flops) *issued_flops = 2.0 * (double)g.total_pairs * (p.cin / 16) * (UP ? 4 : KS * KS) * Cfg::MT * 256.0 * 3.0 * NT * 16.0;
   const long long clusters = g.total_pairs < sm_count / 2 ? g.total_pairs : sm_count / 2;
-  conv_tc2_kernel<NT, KS, UP><<<(int)clusters * 2, T2_THREADS, Cfg::SMEM_BYTES, s>>>(*ta, *w0, *w1, p, g);
+  if (p.host_bn == nullptr) return cudaErrorInvalidValue;
+  conv_tc2_kernel<NT, KS, UP, WRES><<<(int)clusters * 2, T2_THREADS, Cfg::SMEM_BYTES, s>>>(*ta, *w0, *w1, p, g, *p.host_bn);
   return cudaGetLastError();
 }
 
@@ -580,19 +586,21 @@ int tc2_flat_rows(int in_row, int pad_or_up, int up) {
 int tc2_stage_blocks(int up) { return up ? 4 : 3; }
 
 cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const void* tmap_a, const void* tmap_w0, const void* tmap_w1,
-                            int sm_count, cudaStream_t s) {
+                            int sm_count, cudaStream_t s, double* issued_flops) {
   const CUtensorMap* ta = reinterpret_cast<const CUtensorMap*>(tmap_a);
   const CUtensorMap* w0 = reinterpret_cast<const CUtensorMap*>(tmap_w0);
   const CUtensorMap* w1 = reinterpret_cast<const CUtensorMap*>(tmap_w1);
   const int nt = p.cout_total / n_slices;
   if (p.ksize == 1) return cudaErrorInvalidValue;      // the 1x1 heads stay on the single-CTA kernel
   if (up) {
-    if (nt == 64) return launch_pair<64, 3, true>(p, n_slices, ta, w0, w1, sm_count, s);
-    if (nt == 128) return launch_pair<128, 3, true>(p, n_slices, ta, w0, w1, sm_count, s);
+    if (nt == 64) return launch_pair<64, 3, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+    if (nt == 128) return launch_pair<128, 3, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
     return cudaErrorInvalidValue;
   }
-  if (nt == 64) return launch_pair<64, 3, false>(p, n_slices, ta, w0, w1, sm_count, s);
-  if (nt == 128) return launch_pair<128, 3, false>(p, n_slices, ta, w0, w1, sm_count, s);
+  static const bool wres_ok = [] { const char* v = getenv("DCU_WRES"); return !v || atoi(v) != 0; }();
+  if (nt == 64 && n_slices == 1 && p.cin == 64 && wres_ok) return launch_pair<64, 3, false, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+  if (nt == 64) return launch_pair<64, 3, false>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+  if (nt == 128) return launch_pair<128, 3, false>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
   return cudaErrorInvalidValue;
 }
 

@@ -58,6 +58,7 @@ struct Layer3x3 {
   float up_scale = 1.f;
   int tc_nt = 0;              // N per CTA pass for the tcgen05 kernel (64 / 128), 0 = unsupported
   DevBuf bias, alpha, beta;   // [cout]
+  TcBn host_bn{};             // the same three vectors, passed by value to the pair kernel
 };
 
 struct FirstLayer {
@@ -289,7 +290,8 @@ struct DcuEngine {
   DevBuf ref_head_w; float ref_head_b = 0.f;
 
   DevBuf lut;                   // [256] (x-128)/255
-  int mb1 = 32, mb2 = 256, rp = 1024;   // micro-batch sizes: full-res layers, low-res layers, RefineNet patches
+  int mb1 = 32, mb2 = 256, rp = 4096;   // micro-batch sizes: full-res layers, low-res layers, RefineNet patches
+  int rp_plain = 1024;                  // RefineNet chunk when the upsampled tensors are materialised
   DevBuf act[2];                // ping-pong activation buffers
   DevBuf c1[2];                 // conv1a outputs, double-buffered: conv1a of micro-batch i+1 (HBM-write bound, side stream)
                                 // overlaps conv1b/2a/2b of micro-batch i (tensor bound, caller's stream)
@@ -307,7 +309,7 @@ struct DcuEngine {
   DevBuf bgr;                   // [max_batch][H][W][3] staging for the BGR entry point (allocated on first use)
   unsigned int epoch = 1;
   // optional per-launch event timing (dcu_profile_*)
-  struct ProfRec { cudaEvent_t a, b; double work; int cls; int shape[5]; };   // shape: cin, cout, hout, wout, n
+  struct ProfRec { cudaEvent_t a, b; double work; int cls; int shape[5]; double issued; };   // shape: cin, cout, hout, wout, n
   bool profiling = false;
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
@@ -317,13 +319,14 @@ struct DcuEngine {
   }
   void prof_begin(int cls, double work, cudaStream_t s, int cin = 0, int cout = 0, int hout = 0, int wout = 0, int n = 0) {
     if (!profiling) return;
-    ProfRec r{get_event(), get_event(), work, cls, {cin, cout, hout, wout, n}};
+    ProfRec r{get_event(), get_event(), work, cls, {cin, cout, hout, wout, n}, 0.0};
     cudaEventRecord(r.a, s);
     prof.push_back(r);
   }
-  void prof_end(cudaStream_t s) {
+  void prof_end(cudaStream_t s, double issued = 0.0) {
     if (!profiling) return;
     cudaEventRecord(prof.back().b, s);
+    prof.back().issued = issued;
   }
   // pinned staging (host entry point)
   uint8_t* h_frames = nullptr; int32_t* h_counts = nullptr; int32_t* h_offsets = nullptr;
@@ -398,6 +401,13 @@ int build_3x3(Layer3x3& l, std::vector<const DcuConvLayer*> parts, int pad, int 
   CK(upload(l.bias, concat(bs, couts)));
   CK(upload(l.alpha, concat(as, couts)));
   CK(upload(l.beta, concat(es, couts)));
+  if (l.cout > 512) return fail(DCU_ERR_INVALID, "3x3 layer with more than 512 output channels");
+  {
+    const std::vector<float> hb = concat(bs, couts), ha = concat(as, couts), he = concat(es, couts);
+    std::memcpy(l.host_bn.v[0], hb.data(), hb.size() * 4);
+    std::memcpy(l.host_bn.v[1], ha.data(), ha.size() * 4);
+    std::memcpy(l.host_bn.v[2], he.data(), he.size() * 4);
+  }
   l.tc_nt = tc_supported_shape(cin, l.cout);
   if (l.tc_nt > 0) {
     l.tc_scale = tc_weight_scale(ws, couts, cin);
@@ -492,10 +502,12 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
   p.stats = g_tc_stats;
   p.wscale_inv = (impl == DCU_CONV_TCGEN05) ? 1.0f / (up_in ? l.up_scale : l.tc_scale) : 1.0f;
   p.ksize = 3;
+  p.host_bn = &l.host_bn;
   if (fin) { p.flat_in = 1; p.in_period = fin->period; p.in_row = fin->row; }
   if (lout) p.out_layout = *lout;
   if (n <= 0) return DCU_OK;
   e->prof_begin(0, 2.0 * 9.0 * l.cin * l.cout * (double)p.hout * p.wout * n, s, l.cin, l.cout, p.hout, p.wout, n);
+  double issued = 0.0;
   if (impl == DCU_CONV_TCGEN05) {
     if (l.tc_nt == 0) return fail(DCU_ERR_UNSUPPORTED, "layer shape not supported by the tcgen05 kernel");
     const TcGeom g = tc_geom(l.tc_nt, p.hout, p.wout);
@@ -507,14 +519,14 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
     if (rc) return rc;
     if (fuse_up && !e->tc_pair) return fail(DCU_ERR_INVALID, "upsample fusion needs the CTA-pair kernel");
     cudaError_t ce = e->tc_pair
-                         ? (up_in ? launch_conv_tc2(p, l.cout / l.tc_nt, 1, &tm, &l.wmap_up[0], &l.wmap_up[1], e->sm_count, s)
-                                  : launch_conv_tc2(p, l.cout / l.tc_nt, 0, &tm, &l.wmap2[0], &l.wmap2[1], e->sm_count, s))
+                         ? (up_in ? launch_conv_tc2(p, l.cout / l.tc_nt, 1, &tm, &l.wmap_up[0], &l.wmap_up[1], e->sm_count, s, &issued)
+                                  : launch_conv_tc2(p, l.cout / l.tc_nt, 0, &tm, &l.wmap2[0], &l.wmap2[1], e->sm_count, s, &issued))
                          : launch_conv3x3_tc(p, l.w_tc.as<float>(), l.cout / l.tc_nt, l.tc_copies, &tm, e->sm_count, s);
     if (ce != cudaSuccess) return fail(DCU_ERR_CUDA, std::string("tcgen05 conv launch: ") + cudaGetErrorString(ce));
   } else {
     launch_conv3x3_ffma(p, l.w_ffma.as<float>(), s);
   }
-  e->prof_end(s);
+  e->prof_end(s, issued);
   e->launches++;
   CK(cudaGetLastError());
   return DCU_OK;
@@ -644,13 +656,14 @@ static int refine_run(DcuEngine* e, const float* patches, const int32_t* xy, int
   float* a0 = e->act[0].as<float>();
   float* a1 = e->act[1].as<float>();
   int rc;
-  for (int p0 = 0; p0 < p; p0 += e->rp) {
-    const int m = std::min(e->rp, p - p0);
+  // tcgen05 pair kernel: the three 2x upsamplings are never materialised (run_3x3: fuse_up)
+  const bool fu = e->fuse_up && e->tc_pair && e->conv_impl == DCU_CONV_TCGEN05 && e->ref[5].ups_in && e->ref[7].ups_in &&
+                  e->ref[9].ups_in;
+  const int chunk = fu ? e->rp : e->rp_plain;
+  for (int p0 = 0; p0 < p; p0 += chunk) {
+    const int m = std::min(chunk, p - p0);
     unsigned long long* keys = e->keys.as<unsigned long long>() + p0;
     CK(cudaMemsetAsync(keys, 0, (size_t)m * sizeof(unsigned long long), s));
-    // tcgen05 pair kernel: the three 2x upsamplings are never materialised (run_3x3: fuse_up)
-    const bool fu = e->fuse_up && e->tc_pair && e->conv_impl == DCU_CONV_TCGEN05 && e->ref[5].ups_in && e->ref[7].ups_in &&
-                    e->ref[9].ups_in;
     if (fu && e->flat && e->flat8[0].p) {
       // small maps as F2 runs (conv_tc2.cu FLAT mode): 22x22 and 20x20 dense, 8x8 in 9x9 cells with zero gutters (flat8[],
       // zeroed once at creation; only data positions are ever written)
@@ -782,7 +795,7 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   e->mb2 = std::max(e->mb1, (int)std::floor(256.0 / area + 1e-9));
   e->mb1 = std::min(e->mb1, std::max(1, cfg->max_batch));
   e->mb2 = std::min(e->mb2, std::max(e->mb1, cfg->max_batch));
-  e->rp = std::min(1024, std::max(64, cfg->max_patches));
+  e->rp = std::min(4096, std::max(64, cfg->max_patches));
   if (const char* v = getenv("DCU_MB1")) e->mb1 = std::max(1, atoi(v));
   if (const char* v = getenv("DCU_MB2")) e->mb2 = std::max(1, atoi(v));
   if (const char* v = getenv("DCU_RP")) e->rp = std::max(1, atoi(v));
@@ -790,7 +803,10 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   e->mb2 = (e->mb2 / e->mb1) * e->mb1;
   const size_t det_full = (size_t)e->mb1 * 64 * H * W;                       // conv1a out (floats)
   const size_t det_low = (size_t)e->mb2 * 128 * (H / 4) * (W / 4);           // conv3a out
-  const size_t ref_big = e->has_ref ? (size_t)e->rp * 64 * 64 * 64 : 0;      // conv5b upsampled
+  // RefineNet chunk: rp patches when the upsamplings are fused (largest tensor: conv5a output, 64 x 32 x 32), at most 1024
+  // when conv5b's 64 x 64 x 64 upsampled output is materialised (fp32 CUDA-core path, DCU_FUSE_UP=0)
+  e->rp_plain = std::min(e->rp, 1024);
+  const size_t ref_big = e->has_ref ? std::max((size_t)e->rp * 64 * 32 * 32, (size_t)e->rp_plain * 64 * 64 * 64) : 0;
   const size_t act_floats = std::max(std::max(det_full, det_low), ref_big);
   TRYC(e->c1[0].alloc(det_full * 4));
   TRYC(e->c1[1].alloc(det_full * 4));
@@ -877,6 +893,15 @@ int dcu_profile_read(DcuEngine* e, int cls, double* total_ms, double* total_work
     ms += t; work += r.work; ++n;
   }
   *total_ms = ms; *total_work = work; *n_launches = n;
+  return DCU_OK;
+}
+
+int dcu_profile_read_issued(DcuEngine* e, int cls, double* issued_flops) {
+  if (!e || !issued_flops) return fail(DCU_ERR_INVALID, "dcu_profile_read_issued: bad argument");
+  double w = 0;
+  for (auto& r : e->prof)
+    if (r.cls == cls) w += r.issued;
+  *issued_flops = w;
   return DCU_OK;
 }
 

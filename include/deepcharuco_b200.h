@@ -169,6 +169,10 @@ int64_t dcu_launch_count(const DcuEngine* e);
  * ALGORITHMIC work: flops (2*MAC) for classes 0-2, bytes for class 3. */
 int dcu_profile_enable(DcuEngine* e, int on);
 int dcu_profile_read(DcuEngine* e, int cls, double* total_ms, double* total_work, int64_t* n_launches);
+/* Class 0 on the CTA-pair tcgen05 kernel: the flops the tensor pipes actually EXECUTE for the same launches (2 x MACs of all
+ * issued MMAs: three fp16 products per MAC, 4 of 9 taps on upsample-fused layers, padded / wrap-around tile rows included);
+ * 0 for launches of other kernels. */
+int dcu_profile_read_issued(DcuEngine* e, int cls, double* issued_flops);
 /* The individual records since the last enable, in launch order: rec8 [cap][8] doubles
  * {cls, ms, work, cin, cout, hout, wout, n}; *n_records = how many exist (may exceed cap). */
 int dcu_profile_records(DcuEngine* e, int cap, double* rec8, int* n_records);

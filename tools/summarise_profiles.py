@@ -53,7 +53,7 @@ with open(P("launch_list.txt"), "w") as f:
     for k in list(launches)[:48]:
         d = launches[k]
         f.write(f"  {d['name']:30s} {d['grid']:>14s} {d.get('gpu__time_duration.sum',0):9.1f} {d.get('dram__bytes_read.sum',0)/1e6:9.1f} {d.get('dram__bytes_write.sum',0)/1e6:9.1f}\n")
-conv = [a for n, a in agg.items() if "conv3x3_tc" in n]
+conv = [a for n, a in agg.items() if "conv3x3_tc" in n or "conv_tc2" in n]      # single-CTA (1x1 heads) + CTA-pair kernels
 summary = dict(step_kernel_ms=tot / 1e3, launches=len(launches),
                conv3x3_tc=dict(launches=sum(a["n"] for a in conv), ms=sum(a["us"] for a in conv) / 1e3, share=sum(a["us"] for a in conv) / tot,
                                dram_bytes_per_launch=sum(a["rd"] + a["wr"] for a in conv) / max(1, sum(a["n"] for a in conv))),
@@ -72,7 +72,7 @@ KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__registers_p
         "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum"]
-for rep, name in (("conv_tc.ncu-rep", "ncu_conv3x3_tc.txt"), ("small.ncu-rep", "ncu_small_kernels.txt")):
+for rep, name in (("conv_tc.ncu-rep", "ncu_conv_tc2.txt"), ("small.ncu-rep", "ncu_small_kernels.txt")):
     if not os.path.isfile(G(rep)):
         continue
     raw = subprocess.run(["ncu", "-i", G(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
