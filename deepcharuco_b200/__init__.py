@@ -4,4 +4,5 @@ Public surface mirrors /root/reference/src/inference.py; see inference.py in thi
 """
 from .inference import (load_models, infer_image, infer_batch, solve_pnp, pred_to_keypoints,  # noqa: F401
                         extract_patches, pre_bgr_image)
+from .sharding import infer_batch_distributed  # noqa: F401
 from .weights_io import DEFAULT_DEEPC, DEFAULT_REFINENET  # noqa: F401

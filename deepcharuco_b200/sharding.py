@@ -38,3 +38,24 @@ def unpack_results(counts, flat, integer=False):
             out.append(r.astype(np.int64) if integer else r.copy())
             o += c
     return out
+
+
+def infer_batch_distributed(frames, dust_bin_ids, deepc=None, refinenet=None, group=None, local_fn=None):
+    """Multi-GPU `infer_batch` for one process per GPU (torchrun / torch.distributed): every rank passes the SAME (N,H,W)
+    uint8 batch, runs its contiguous shard on its own device and engine, and the per-frame results (tiny: 24 B per corner) are
+    all-gathered as packed arrays, so every rank returns the full list in frame order.  No collective touches the data path
+    (SURVEY.md 8e); the gather moves results only.  `local_fn(frames_shard) -> list` replaces the engine call in CPU tests."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_range(len(frames), rank, world)
+    if local_fn is None:
+        from . import inference
+        local_fn = lambda fr: inference.infer_batch(fr, dust_bin_ids, deepc, refinenet)
+    mine = local_fn(frames[lo:hi]) if hi > lo else []
+    integer = refinenet is None and deepc is not None
+    if world == 1:
+        return list(mine)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, pack_results(mine), group=group)
+    return merge_shards([unpack_results(c, f, integer=integer) for c, f in gathered])

@@ -35,6 +35,13 @@ def _worker(rank, world, port, out_dir):
     dist.all_gather_object(gathered, (counts, flat))
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)          # the timing reduction bench.py does (max over ranks)
+    # the user-facing wrapper: same batch on every rank, full result list on every rank
+    frames = np.arange(n, dtype=np.int64)          # stand-in "frames": indices into the golden logits
+    full = sharding.infer_batch_distributed(frames, 16, local_fn=lambda fr: [_frame_result(loc[i % 3], ids[i % 3]) for i in fr])
+    assert len(full) == n
+    for i, got in enumerate(full):
+        want = _frame_result(loc[i % 3], ids[i % 3])
+        assert got.shape == want.shape and np.array_equal(np.asarray(got, np.float64), np.asarray(want, np.float64))
     if rank == 0:
         merged = sharding.merge_shards([sharding.unpack_results(c, f, integer=True) for c, f in gathered])
         np.savez(os.path.join(out_dir, "merged.npz"), n=len(merged), tmax=t.numpy(),
