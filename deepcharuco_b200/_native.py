@@ -19,7 +19,7 @@ CONV_DEFAULT = CONV_TCGEN05   # tcgen05 tensor-core path (fp16 hi/lo split); CON
 EXPORTS = [
     "dcu_create", "dcu_destroy", "dcu_detector_forward", "dcu_detector_forward_f32", "dcu_extract_patches",
     "dcu_decode_gather", "dcu_refine_forward", "dcu_infer_batch", "dcu_infer_batch_host", "dcu_infer_batch_host_bgr", "dcu_bgr_to_gray",
-    "dcu_debug_conv_layer", "dcu_debug_tc_stats", "dcu_set_conv_impl", "dcu_launch_count", "dcu_profile_enable", "dcu_profile_read", "dcu_profile_read_issued", "dcu_profile_records", "dcu_detector_flops_per_frame",
+    "dcu_debug_conv_layer", "dcu_debug_tc_stats", "dcu_set_conv_impl", "dcu_launch_count", "dcu_profile_enable", "dcu_profile_read", "dcu_profile_read_issued", "dcu_solve_pnp_batch", "dcu_solve_pnp_batch_host", "dcu_profile_records", "dcu_detector_flops_per_frame",
     "dcu_refine_flops_per_patch", "dcu_last_error", "dcu_version",
 ]
 
@@ -75,6 +75,8 @@ def lib():
     L.dcu_profile_enable.argtypes = [vp, i32]
     L.dcu_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     L.dcu_profile_read_issued.argtypes = [vp, i32, C.POINTER(C.c_double)]
+    L.dcu_solve_pnp_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, C.c_double, vp, vp, i32, vp, vp, vp, vp]
+    L.dcu_solve_pnp_batch_host.argtypes = [vp, vp, vp, vp, i32, i32, i32, C.c_double, vp, vp, i32, vp, vp, vp, vp]
     L.dcu_profile_records.argtypes = [vp, i32, vp, C.POINTER(i32)]
     L.dcu_launch_count.argtypes = [vp]
     L.dcu_launch_count.restype = i64
@@ -228,6 +230,40 @@ class Engine:
                                     o["counts"].data_ptr(), o["offsets"].data_ptr(), o["total"].data_ptr(),
                                     o["kpts"].data_ptr(), o["refined"].data_ptr(), stream))
         return o
+
+    def solve_pnp_batch_host(self, counts, kpts, refined, col_count, row_count, square_len, camera_matrix, dist_coeffs, stream=None):
+        """counts int32 [N], kpts int32 [sum,4] (x, y, id, cell), refined float32 [sum,2] or None -> (ret int32 [N], rvec f64 [N,3], tvec f64 [N,3])."""
+        counts = np.ascontiguousarray(counts, np.int32)
+        kpts = np.ascontiguousarray(kpts, np.int32).reshape(-1, 4)
+        n = int(counts.shape[0])
+        assert int(counts.sum()) == kpts.shape[0]
+        ref = None if refined is None else np.ascontiguousarray(refined, np.float32).reshape(-1, 2)
+        cam = np.ascontiguousarray(camera_matrix, np.float64).reshape(3, 3)
+        dist = np.zeros(0) if dist_coeffs is None else np.ascontiguousarray(dist_coeffs, np.float64).reshape(-1)
+        ret, rvec, tvec = np.zeros(n, np.int32), np.zeros((n, 3), np.float64), np.zeros((n, 3), np.float64)
+        check(lib().dcu_solve_pnp_batch_host(self._h, counts.ctypes.data, kpts.ctypes.data, None if ref is None else ref.ctypes.data, n,
+                                             int(col_count), int(row_count), float(square_len), cam.ctypes.data,
+                                             dist.ctypes.data if dist.size else None, int(dist.size), ret.ctypes.data,
+                                             rvec.ctypes.data, tvec.ctypes.data, stream))
+        return ret, rvec, tvec
+
+    def solve_pnp_batch_device(self, n, col_count, row_count, square_len, camera_matrix, dist_coeffs, use_refined=True, stream=None):
+        """Pose of every frame of the last infer_batch_device call, on its device-resident results; returns torch tensors
+        (ret int32 [n], rvec f64 [n,3], tvec f64 [n,3]) on the engine's device."""
+        import torch
+        o = self._dev_out
+        dev = o["counts"].device
+        if "pnp_ret" not in o or o["pnp_ret"].shape[0] < n:
+            o["pnp_ret"] = torch.zeros(self.max_batch, dtype=torch.int32, device=dev)
+            o["pnp_rvec"] = torch.zeros((self.max_batch, 3), dtype=torch.float64, device=dev)
+            o["pnp_tvec"] = torch.zeros((self.max_batch, 3), dtype=torch.float64, device=dev)
+        cam = np.ascontiguousarray(camera_matrix, np.float64).reshape(3, 3)
+        dist = np.zeros(0) if dist_coeffs is None else np.ascontiguousarray(dist_coeffs, np.float64).reshape(-1)
+        check(lib().dcu_solve_pnp_batch(self._h, o["counts"].data_ptr(), o["offsets"].data_ptr(), o["kpts"].data_ptr(),
+                                        o["refined"].data_ptr() if use_refined else None, int(n), int(col_count), int(row_count),
+                                        float(square_len), cam.ctypes.data, dist.ctypes.data if dist.size else None, int(dist.size),
+                                        o["pnp_ret"].data_ptr(), o["pnp_rvec"].data_ptr(), o["pnp_tvec"].data_ptr(), stream))
+        return o["pnp_ret"][:n], o["pnp_rvec"][:n], o["pnp_tvec"][:n]
 
     def detector_flops_per_frame(self):
         return float(lib().dcu_detector_flops_per_frame(self._h))

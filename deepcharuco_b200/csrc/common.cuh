@@ -157,6 +157,15 @@ int tc2_flat_rows(int in_row, int pad_or_up, int up);   // FLAT mode: rows of 16
 cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const void* tmap_a, const void* tmap_w0, const void* tmap_w1,
                             int sm_count, cudaStream_t s, double* issued_flops = nullptr);
 
+// batched board pose (pnp.cu): per frame f, corners kpts[offsets[f] .. +counts[f]) (x, y, id, cell), optional refined (x, y)
+struct PnpParams {
+  const int32_t* counts; const int32_t* offsets; const int32_t* kpts; const float* refined;
+  const float* obj;       // [n_obj][2] board coordinates of the inner corners (device)
+  int n, n_obj;
+  int32_t* ret; double* rvec; double* tvec;     // [n], [n][3], [n][3]
+};
+void launch_pnp_batch(const PnpParams& q, const double* camera9, const double* dist, int n_dist, cudaStream_t s);
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace dcu

@@ -306,6 +306,8 @@ struct DcuEngine {
   DevBuf heads;                 // (Pa|Da) output for mb2 frames
   DevBuf loc, ids;              // [mb2] logits when the caller does not want them
   DevBuf counts, offsets, total, kpts, patches, keys, refined, scan_state, frames;
+  DevBuf pnp_obj;               // [n_obj][2] board corner table of the last solve_pnp geometry
+  int pnp_cols = 0, pnp_rows = 0; double pnp_sq = 0.0;
   DevBuf bgr;                   // [max_batch][H][W][3] staging for the BGR entry point (allocated on first use)
   unsigned int epoch = 1;
   // optional per-launch event timing (dcu_profile_*)
@@ -336,7 +338,7 @@ struct DcuEngine {
     if (side) cudaStreamDestroy(side);
     if (ev_start) cudaEventDestroy(ev_start);
     for (int i = 0; i < 2; ++i) { if (ev_done[i]) cudaEventDestroy(ev_done[i]); if (ev_free[i]) cudaEventDestroy(ev_free[i]); }
-    DevBuf* all[] = {&flat8[0], &flat8[1], &flat8[2], &bgr, &c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
+    DevBuf* all[] = {&pnp_obj, &flat8[0], &flat8[1], &flat8[2], &bgr, &c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
                      &ids, &counts, &offsets, &total, &kpts, &patches, &keys, &refined, &scan_state, &frames};
     for (DevBuf* b : all) b->release();
     FirstLayer* fl[] = {&det_first, &ref_first};
@@ -1122,6 +1124,82 @@ static int infer_batch_host_impl(DcuEngine* e, const uint8_t* frames_host, int n
   if (total > e->cfg.max_patches)
     return fail(DCU_ERR_CAPACITY, "corner count " + std::to_string(total) + " exceeds max_patches " +
                                       std::to_string(e->cfg.max_patches));
+  return DCU_OK;
+}
+
+// ---- batched solve_pnp (inference.py:15-29) ----
+static int pnp_object_table(DcuEngine* e, int col_count, int row_count, double square_len) {
+  // object_points[:, :2] = meshgrid(arange(1,row_count), arange(1,col_count)).reshape(2,-1).T * square_len  (float32 storage):
+  // point p -> ((p % (row_count-1)) + 1, (p / (row_count-1)) + 1) * square_len
+  if (col_count < 2 || row_count < 2) return fail(DCU_ERR_INVALID, "solve_pnp: board needs >= 2 x 2 squares");
+  if (e->pnp_cols == col_count && e->pnp_rows == row_count && e->pnp_sq == square_len && e->pnp_obj.p) return DCU_OK;
+  const int n_obj = (col_count - 1) * (row_count - 1);
+  std::vector<float> t((size_t)n_obj * 2);
+  for (int p = 0; p < n_obj; ++p) {
+    t[2 * p] = (float)((double)((p % (row_count - 1)) + 1) * square_len);
+    t[2 * p + 1] = (float)((double)((p / (row_count - 1)) + 1) * square_len);
+  }
+  e->pnp_obj.release();
+  CK(upload(e->pnp_obj, t));
+  e->pnp_cols = col_count; e->pnp_rows = row_count; e->pnp_sq = square_len;
+  return DCU_OK;
+}
+
+int dcu_solve_pnp_batch(DcuEngine* e, const int32_t* counts_dev, const int32_t* offsets_dev, const int32_t* kpts_dev,
+                        const float* refined_dev, int n, int col_count, int row_count, double square_len,
+                        const double* camera_matrix9, const double* dist_coeffs, int n_dist, int32_t* ret_dev,
+                        double* rvec_dev, double* tvec_dev, void* stream) {
+  if (!e || !counts_dev || !offsets_dev || !kpts_dev || !camera_matrix9 || !ret_dev || !rvec_dev || !tvec_dev || n < 0 ||
+      n_dist < 0 || (n_dist > 0 && !dist_coeffs))
+    return fail(DCU_ERR_INVALID, "dcu_solve_pnp_batch: bad argument");
+  if (n_dist > 8) return fail(DCU_ERR_UNSUPPORTED, "dcu_solve_pnp_batch: at most 8 distortion coefficients (k1 k2 p1 p2 k3 k4 k5 k6)");
+  CK(cudaSetDevice(e->cfg.device));
+  int rc = pnp_object_table(e, col_count, row_count, square_len);
+  if (rc) return rc;
+  PnpParams q{};
+  q.counts = counts_dev; q.offsets = offsets_dev; q.kpts = kpts_dev; q.refined = refined_dev;
+  q.obj = e->pnp_obj.as<float>(); q.n = n; q.n_obj = (col_count - 1) * (row_count - 1);
+  q.ret = ret_dev; q.rvec = rvec_dev; q.tvec = tvec_dev;
+  launch_pnp_batch(q, camera_matrix9, dist_coeffs, n_dist, (cudaStream_t)stream);
+  if (n > 0) e->launches++;
+  CK(cudaGetLastError());
+  return DCU_OK;
+}
+
+int dcu_solve_pnp_batch_host(DcuEngine* e, const int32_t* counts_host, const int32_t* kpts_host, const float* refined_host, int n,
+                             int col_count, int row_count, double square_len, const double* camera_matrix9,
+                             const double* dist_coeffs, int n_dist, int32_t* ret_host, double* rvec_host, double* tvec_host,
+                             void* stream) {
+  if (!e || !counts_host || !kpts_host || !ret_host || !rvec_host || !tvec_host || n < 0)
+    return fail(DCU_ERR_INVALID, "dcu_solve_pnp_batch_host: bad argument");
+  if (n == 0) return DCU_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<int32_t> offs(n);
+  long long total = 0;
+  for (int i = 0; i < n; ++i) { if (counts_host[i] < 0) return fail(DCU_ERR_INVALID, "negative count"); offs[i] = (int32_t)total; total += counts_host[i]; }
+  DevBuf c, o, k, r, ret, rv, tv;
+  auto freeall = [&]() { c.release(); o.release(); k.release(); r.release(); ret.release(); rv.release(); tv.release(); };
+#define PK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { freeall(); return fail(DCU_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); } } while (0)
+  PK(c.alloc((size_t)n * 4)); PK(o.alloc((size_t)n * 4)); PK(k.alloc((size_t)total * 16)); PK(ret.alloc((size_t)n * 4));
+  PK(rv.alloc((size_t)n * 24)); PK(tv.alloc((size_t)n * 24));
+  PK(cudaMemcpyAsync(c.p, counts_host, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  PK(cudaMemcpyAsync(o.p, offs.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  if (total > 0) PK(cudaMemcpyAsync(k.p, kpts_host, (size_t)total * 16, cudaMemcpyHostToDevice, s));
+  if (refined_host) {
+    PK(r.alloc((size_t)total * 8));
+    if (total > 0) PK(cudaMemcpyAsync(r.p, refined_host, (size_t)total * 8, cudaMemcpyHostToDevice, s));
+  }
+  int rc = dcu_solve_pnp_batch(e, c.as<int32_t>(), o.as<int32_t>(), k.as<int32_t>(), refined_host ? r.as<float>() : nullptr, n,
+                               col_count, row_count, square_len, camera_matrix9, dist_coeffs, n_dist, ret.as<int32_t>(),
+                               rv.as<double>(), tv.as<double>(), stream);
+  if (rc) { freeall(); return rc; }
+  PK(cudaMemcpyAsync(ret_host, ret.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+  PK(cudaMemcpyAsync(rvec_host, rv.p, (size_t)n * 24, cudaMemcpyDeviceToHost, s));
+  PK(cudaMemcpyAsync(tvec_host, tv.p, (size_t)n * 24, cudaMemcpyDeviceToHost, s));
+  PK(cudaStreamSynchronize(s));
+#undef PK
+  freeall();
   return DCU_OK;
 }
 

@@ -53,6 +53,7 @@ class _Context:
         self.n_ids, self.device = int(n_ids), int(device)
         self.conv_impl = _default_conv_impl()
         self._engines = {}
+        _CONTEXTS.append(self)
 
     def engine(self, height, width, max_batch=1, max_patches=None) -> N.Engine:
         key = (int(height), int(width))
@@ -309,6 +310,45 @@ def solve_pnp(keypoints, col_count, row_count, square_len, camera_matrix, dist_c
     object_points_found = object_points[keypoints[:, 2].astype(int)]
     ret, rvec, tvec = cv2.solvePnP(object_points_found, image_points, camera_matrix, dist_coeffs)
     return ret, rvec, tvec
+
+
+def solve_pnp_batch(keypoints_list, col_count, row_count, square_len, camera_matrix, dist_coeffs, deepc: "DeepcHandle" = None):
+    """`solve_pnp` for every frame of a batch in ONE GPU launch (the loop at pose_estimation.py:58-63).
+
+    keypoints_list: what `infer_batch` returns (per frame a (K,3) array [x, y, id] or an empty array).  Returns a list of
+    `(ret, rvec, tvec)` with the reference's conventions: `(False, None, None)` below 4 corners (inference.py:16-17), else
+    `ret` bool and rvec / tvec as (3,1) float64 like cv2.solvePnP.  The solver restates cv2's SOLVEPNP_ITERATIVE for planar
+    points in fp64 (csrc/pnp_core.cuh): same minimum as cv2 to ~1e-7 on well-conditioned frames; `solve_pnp` (host cv2)
+    stays the drop-in default.  `deepc` selects the engine (device); any loaded model's engine is used when omitted."""
+    ctx = deepc._ctx if deepc is not None else _any_context()
+    eng = next(iter(ctx._engines.values())) if ctx._engines else ctx.engine(240, 320)
+    n = len(keypoints_list)
+    if n == 0:
+        return []
+    counts = np.array([0 if np.asarray(k).size == 0 else np.asarray(k).shape[0] for k in keypoints_list], np.int32)
+    rows = [np.asarray(k, np.float64).reshape(-1, 3) for k in keypoints_list if np.asarray(k).size]
+    flat = np.concatenate(rows, 0) if rows else np.zeros((0, 3))
+    kpts = np.zeros((flat.shape[0], 4), np.int32)
+    kpts[:, 2] = flat[:, 2].astype(int)                                         # keypoints[:, 2].astype(int), inference.py:26
+    refined = flat[:, :2].astype(np.float32)                                    # keypoints[:, :2].astype(np.float32), :25
+    ret, rvec, tvec = eng.solve_pnp_batch_host(counts, kpts, refined, col_count, row_count, square_len, camera_matrix, dist_coeffs)
+    out = []
+    for i in range(n):
+        if counts[i] < 4:
+            out.append((False, None, None))
+        else:
+            out.append((bool(ret[i]), rvec[i].reshape(3, 1).copy(), tvec[i].reshape(3, 1).copy()))
+    return out
+
+
+_CONTEXTS = []
+
+
+def _any_context():
+    live = [c for c in _CONTEXTS if c is not None]
+    if not live:
+        raise RuntimeError("solve_pnp_batch needs a loaded model (load_models) to pick a device")
+    return live[-1]
 
 
 def draw_inner_corners(img, corners, ids, radius=2, draw_ids=True, color=(0, 0, 255)):

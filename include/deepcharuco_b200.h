@@ -156,6 +156,24 @@ int dcu_debug_conv_layer(DcuEngine* e, int net, int layer, int conv_impl, const 
  * total / wait MMA), summed over CTAs; out8 (may be NULL) receives the counters accumulated so far. */
 int dcu_debug_tc_stats(DcuEngine* e, int enable, uint64_t* out8);
 
+/* Batched board pose: inference.solve_pnp (inference.py:15-29; called per frame by pose_estimation.py:61-63) for all frames
+ * of a batch in one launch, directly on the engine's result buffers (dcu_infer_batch outputs): per frame f the corners
+ * kpts[offsets[f] .. offsets[f]+counts[f]) with image points = refined (x, y) (or the integer pixels when refined_dev is
+ * NULL) and object points = the board's inner-corner table the reference builds from (col_count, row_count, square_len).
+ * Restates cv2.solvePnP(SOLVEPNP_ITERATIVE) for coplanar points in fp64 (homography start + Levenberg-Marquardt on the
+ * pixel reprojection error, OpenCV's distortion model with up to 8 coefficients k1 k2 p1 p2 k3 k4 k5 k6).
+ * ret[f] = 1 on success, 0 for frames with < 4 corners (the reference returns (False, None, None)) or a degenerate /
+ * out-of-range configuration; rvec / tvec are [n][3] doubles (zeros where ret == 0).  camera_matrix9 (row-major 3x3) and
+ * dist_coeffs are HOST pointers.  The _host variant takes and returns host arrays (kpts_host packed [sum counts][4]). */
+int dcu_solve_pnp_batch(DcuEngine* e, const int32_t* counts_dev, const int32_t* offsets_dev, const int32_t* kpts_dev,
+                        const float* refined_dev, int n, int col_count, int row_count, double square_len,
+                        const double* camera_matrix9, const double* dist_coeffs, int n_dist, int32_t* ret_dev,
+                        double* rvec_dev, double* tvec_dev, void* stream);
+int dcu_solve_pnp_batch_host(DcuEngine* e, const int32_t* counts_host, const int32_t* kpts_host, const float* refined_host, int n,
+                             int col_count, int row_count, double square_len, const double* camera_matrix9,
+                             const double* dist_coeffs, int n_dist, int32_t* ret_host, double* rvec_host, double* tvec_host,
+                             void* stream);
+
 /* Select the 3x3 conv implementation after creation (DCU_CONV_*). */
 int dcu_set_conv_impl(DcuEngine* e, int conv_impl);
 

@@ -1,7 +1,2 @@
-(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8) > gpurun_out/s6_pytest.log 2>&1; tail -3 gpurun_out/s6_pytest.log
-python tools/layer_table.py --batch 256 --json gpurun_out/s6_layers.json > gpurun_out/s6_layers.log 2>&1; tail -22 gpurun_out/s6_layers.log | cut -c1-210
-b() { python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$1', round(d['value']), round(d['e2e']['value']), round(d['roofline']['achieved'],1), round(d['roofline']['issued_tflops'],1), d['clocks']['sm_mhz'], d['clocks']['power_w_max'])"; }
-b base
-DCU_WRES=0 b nowres
-b base
-DCU_WRES=0 b nowres
+(timeout 600 python -m pytest tests/test_gpu_pnp.py -m gpu -x -q -s 2>&1 | tail -15) > gpurun_out/s7_pnp.log 2>&1; cat gpurun_out/s7_pnp.log
+(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5) > gpurun_out/s7_pytest.log 2>&1; tail -3 gpurun_out/s7_pytest.log
