@@ -1,2 +1,2 @@
-(timeout 600 python -m pytest tests/test_gpu_pnp.py -m gpu -x -q -s 2>&1 | tail -15) > gpurun_out/s7_pnp.log 2>&1; cat gpurun_out/s7_pnp.log
-(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5) > gpurun_out/s7_pytest.log 2>&1; tail -3 gpurun_out/s7_pytest.log
+python tools/bench_configs.py --iters 5 --out gpurun_out/r1c_configs.json > gpurun_out/r1c_configs.log 2>&1; tail -50 gpurun_out/r1c_configs.log
+python tools/bench_single_frame.py --cpu > gpurun_out/r1c_single_frame.json 2> gpurun_out/r1c_single_frame.err; cat gpurun_out/r1c_single_frame.json

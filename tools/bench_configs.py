@@ -48,6 +48,18 @@ ms = timed(lambda: eng.infer_batch_device(frames.data_ptr(), 256, 16, True, None
 k = int(eng._dev_out["total"].item())
 res["config3_full_b256_320x240"] = dict(ms=ms, frames_per_s=256 / ms * 1e3, corners=k,
                                          tflops_alg=(256 * eng.detector_flops_per_frame() + k * eng.refine_flops_per_patch()) / ms / 1e9)
+# board pose for the 256 frames of config 3, GPU batch (on the device-resident results) vs the reference's
+# per-frame cv2.solvePnP loop on one host core (inference.py:15-29)
+import time
+import deepcharuco_b200 as dc
+Kc = np.array([[300.0, 0, 160], [0, 300.0, 120], [0, 0, 1]])
+ms = timed(lambda: eng.solve_pnp_batch_device(256, 5, 5, 0.01, Kc, np.zeros(5), True, None), 20)
+host_rows = dc.inference._rows_to_frames(*eng.infer_batch_host(frames.cpu().numpy(), 16, True))
+t0 = time.time()
+for kp in host_rows:
+    dc.solve_pnp(kp, 5, 5, 0.01, Kc, np.zeros(5)) if kp.size else None
+cv_ms = (time.time() - t0) * 1e3
+res["pnp_b256"] = dict(gpu_ms=ms, gpu_frames_per_s=256 / ms * 1e3, cv2_host_loop_ms=cv_ms, cv2_frames_per_s=256 / cv_ms * 1e3)
 # config 4: RefineNet microbench, 16384 real patches (the engine's own gather output, cycled)
 o = eng._dev_out
 patches_src = torch.empty((k, 24, 24), device="cuda")
