@@ -42,6 +42,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dcu {
@@ -524,6 +526,11 @@ void tc_tile_arrangement(int nt, int hout, int wout, int* tr, int* tc) {
 int tc_supported_shape(int cin, int cout) {
   if (cin % 16 != 0 || cin > 256) return 0;
   if (cout == 64) return 64;
+  // 64 -> 128 layers (detector conv3a, RefineNet conv2a): K is only 4 chunks deep, so the un-overlapped epilogue of the single
+  // NT = 128 accumulator set costs more than reading the activations twice with double-buffered NT = 64 slices (DCU_NT64=0: off)
+  static const int nt64 = [] { const char* v = getenv("DCU_NT64"); return v ? atoi(v) : 1; }();
+  if (nt64 >= 1 && cin == 64 && cout == 128) return 64;
+  if (nt64 >= 2 && cout % 64 == 0 && cout <= 512) return 64;      // experiment: every layer in double-buffered 64-channel slices
   if (cout % 128 == 0 && cout <= 512) return 128;
   return 0;
 }
