@@ -310,6 +310,15 @@ struct DcuEngine {
   int pnp_cols = 0, pnp_rows = 0; double pnp_sq = 0.0;
   DevBuf bgr;                   // [max_batch][H][W][3] staging for the BGR entry point (allocated on first use)
   unsigned int epoch = 1;
+  unsigned int epoch_override = 0;      // != 0 while a small-batch graph is captured (replays reset scan_state instead)
+  // Small batches (one frame per call is the reference's own benchmark loop, src/benchmark.py:38-53): ~27 launches of a few
+  // microseconds each are launch-bound, so the whole fixed sequence  H2D -> detector -> decode -> RefineNet on a fixed number of
+  // patch slots -> D2H  is captured once per (n, dust_bin, use_refinenet) and replayed as ONE cudaGraphLaunch.
+  struct SmallGraph { cudaGraphExec_t exec = nullptr; int n = 0, dust = 0, use_ref = 0, pfix = 0; int64_t launches = 0; bool dead = false; };
+  std::vector<SmallGraph> graphs;
+  cudaStream_t gstream = nullptr;       // capture stream
+  bool use_graphs = true;               // DCU_GRAPH=0: always launch kernel by kernel
+  int graph_max_n = 8;
   // optional per-launch event timing (dcu_profile_*)
   struct ProfRec { cudaEvent_t a, b; double work; int cls; int shape[5]; double issued; };   // shape: cin, cout, hout, wout, n
   bool profiling = false;
@@ -336,6 +345,8 @@ struct DcuEngine {
 
   ~DcuEngine() {
     if (side) cudaStreamDestroy(side);
+    for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (gstream) cudaStreamDestroy(gstream);
     if (ev_start) cudaEventDestroy(ev_start);
     for (int i = 0; i < 2; ++i) { if (ev_done[i]) cudaEventDestroy(ev_done[i]); if (ev_free[i]) cudaEventDestroy(ev_free[i]); }
     DevBuf* all[] = {&pnp_obj, &flat8[0], &flat8[1], &flat8[2], &bgr, &c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
@@ -642,7 +653,7 @@ static int decode_group(DcuEngine* e, const float* loc, const float* ids, const 
   d.n = n; d.H = e->cfg.height; d.W = e->cfg.width; d.h = d.H / 8; d.w = d.W / 8; d.n_ids1 = e->cfg.n_ids + 1;
   d.dust_bin = dust_bin; d.append = append; d.counts = counts; d.offsets = offsets; d.total = total; d.kpts = kpts;
   d.patches = patches; d.max_patches = e->cfg.max_patches; d.scan_state = e->scan_state.as<unsigned long long>();
-  d.epoch = e->epoch++;
+  d.epoch = e->epoch_override ? e->epoch_override : e->epoch++;
   // algorithmic bytes: logits read once; + K*(2304 read + 2304 written + 16) added by the caller's K
   e->prof_begin(3, (double)(65 + d.n_ids1) * d.h * d.w * 4.0 * n, s);
   launch_decode_gather(d, s);
@@ -821,6 +832,9 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   if (const char* v = getenv("DCU_OVERLAP_FIRST")) e->overlap_first = atoi(v) != 0;
   if (const char* v = getenv("DCU_TC_PAIR")) e->tc_pair = atoi(v) != 0;
   if (const char* v = getenv("DCU_FUSE_UP")) e->fuse_up = atoi(v) != 0;
+  if (const char* v = getenv("DCU_GRAPH")) e->use_graphs = atoi(v) != 0;
+  if (const char* v = getenv("DCU_GRAPH_MAX_N")) e->graph_max_n = std::max(0, atoi(v));
+  TRYC(cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking));
   if (const char* v = getenv("DCU_FLAT")) e->flat = atoi(v) != 0;
   if (e->has_ref && e->flat)
     for (int i = 0; i < 3; ++i) {
@@ -867,6 +881,12 @@ int dcu_destroy(DcuEngine* e) {
 
 int dcu_set_conv_impl(DcuEngine* e, int impl) {
   if (!e || (impl != DCU_CONV_FFMA && impl != DCU_CONV_TCGEN05)) return fail(DCU_ERR_INVALID, "bad conv_impl");
+  if (impl != e->conv_impl) {           // captured small-batch graphs hold the old kernels
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaDeviceSynchronize());
+    for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    e->graphs.clear();
+  }
   e->conv_impl = impl;
   return DCU_OK;
 }
@@ -1063,6 +1083,86 @@ int dcu_infer_batch_host_bgr(DcuEngine* e, const uint8_t* frames_host, int n, in
                                refined_host, stream);
 }
 
+// Small-batch path: returns 1 if it did not handle the call (caller continues kernel by kernel), else a DCU_* status.
+static int infer_small_graph(DcuEngine* e, const uint8_t* frames_host, int n, int dust_bin_ids, int use_refinenet,
+                             int32_t* counts_host, int32_t* offsets_host, int32_t* total_host, int32_t* kpts_host,
+                             float* refined_host, cudaStream_t s) {
+  const int H = e->cfg.height, W = e->cfg.width;
+  const int pfix = std::min(32 * n, e->cfg.max_patches);
+  DcuEngine::SmallGraph* g = nullptr;
+  for (auto& x : e->graphs)
+    if (x.n == n && x.dust == dust_bin_ids && x.use_ref == use_refinenet) g = &x;
+  if (!g) {            // first call of this shape runs kernel by kernel (sets function attributes, allocates lazily)
+    if (e->graphs.size() >= 64) return 1;
+    DcuEngine::SmallGraph x; x.n = n; x.dust = dust_bin_ids; x.use_ref = use_refinenet; x.pfix = pfix;
+    e->graphs.push_back(x);
+    return 1;
+  }
+  if (g->dead) return 1;
+  if (!g->exec) {
+    cudaStream_t gs = e->gstream;
+    if (cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); g->dead = true; return 1; }
+    const int64_t l0 = e->launches;
+    e->epoch_override = 0x3ffffff0u;
+    int rc = DCU_OK;
+    cudaError_t ce = cudaMemcpyAsync(e->frames.p, e->h_frames, (size_t)n * H * W, cudaMemcpyHostToDevice, gs);
+    if (ce == cudaSuccess) rc = detector_group(e, e->frames.as<uint8_t>(), nullptr, n, e->loc.as<float>(), e->ids.as<float>(), gs);
+    if (ce == cudaSuccess && rc == DCU_OK) ce = cudaMemsetAsync(e->scan_state.p, 0, (size_t)n * 8, gs);
+    if (ce == cudaSuccess && rc == DCU_OK)
+      rc = decode_group(e, e->loc.as<float>(), e->ids.as<float>(), e->frames.as<uint8_t>(), n, dust_bin_ids, 0, e->counts.as<int32_t>(),
+                        e->offsets.as<int32_t>(), e->total.as<int32_t>(), e->kpts.as<int32_t>(),
+                        use_refinenet ? e->patches.as<float>() : nullptr, gs);
+    if (ce == cudaSuccess && rc == DCU_OK && use_refinenet)
+      rc = refine_run(e, e->patches.as<float>(), e->kpts.as<int32_t>(), 4, pfix, nullptr, e->refined.as<float>(), nullptr, gs);
+    if (ce == cudaSuccess && rc == DCU_OK) ce = cudaMemcpyAsync(e->h_total, e->total.p, 4, cudaMemcpyDeviceToHost, gs);
+    if (ce == cudaSuccess && rc == DCU_OK) ce = cudaMemcpyAsync(e->h_counts, e->counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, gs);
+    if (ce == cudaSuccess && rc == DCU_OK) ce = cudaMemcpyAsync(e->h_offsets, e->offsets.p, (size_t)n * 4, cudaMemcpyDeviceToHost, gs);
+    if (ce == cudaSuccess && rc == DCU_OK) ce = cudaMemcpyAsync(e->h_kpts, e->kpts.p, (size_t)pfix * 16, cudaMemcpyDeviceToHost, gs);
+    if (ce == cudaSuccess && rc == DCU_OK && use_refinenet)
+      ce = cudaMemcpyAsync(e->h_refined, e->refined.p, (size_t)pfix * 8, cudaMemcpyDeviceToHost, gs);
+    e->epoch_override = 0;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ee = cudaStreamEndCapture(gs, &graph);
+    g->launches = e->launches - l0;
+    e->launches = l0;
+    if (ce != cudaSuccess || rc != DCU_OK || ee != cudaSuccess || !graph ||
+        cudaGraphInstantiate(&g->exec, graph, 0) != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      g->exec = nullptr; g->dead = true;
+      return 1;
+    }
+    cudaGraphDestroy(graph);
+  }
+  std::memcpy(e->h_frames, frames_host, (size_t)n * H * W);
+  CK(cudaGraphLaunch(g->exec, s));
+  e->launches += g->launches;
+  CK(cudaStreamSynchronize(s));
+  const int total = e->h_total[0];
+  const int kept = std::min(total, e->cfg.max_patches);
+  if (total > g->pfix) {
+    // crowded frames: more corners than the graph's patch slots -> finish kernel by kernel on the device-resident decode output
+    if (use_refinenet) {
+      int rc = refine_run(e, e->patches.as<float>(), e->kpts.as<int32_t>(), 4, kept, nullptr, e->refined.as<float>(), nullptr, s);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(e->h_refined, e->refined.p, (size_t)kept * 8, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaMemcpyAsync(e->h_kpts, e->kpts.p, (size_t)kept * 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  std::memcpy(counts_host, e->h_counts, (size_t)n * 4);
+  std::memcpy(offsets_host, e->h_offsets, (size_t)n * 4);
+  if (kept > 0) {
+    std::memcpy(kpts_host, e->h_kpts, (size_t)kept * 16);
+    if (use_refinenet) std::memcpy(refined_host, e->h_refined, (size_t)kept * 8);
+  }
+  *total_host = total;
+  if (total > e->cfg.max_patches)
+    return fail(DCU_ERR_CAPACITY, "corner count " + std::to_string(total) + " exceeds max_patches " +
+                                      std::to_string(e->cfg.max_patches));
+  return DCU_OK;
+}
+
 static int infer_batch_host_impl(DcuEngine* e, const uint8_t* frames_host, int n, int channels, int dust_bin_ids, int use_refinenet,
                                  int32_t* counts_host, int32_t* offsets_host, int32_t* total_host, int32_t* kpts_host,
                                  float* refined_host, void* stream) {
@@ -1076,6 +1176,11 @@ static int infer_batch_host_impl(DcuEngine* e, const uint8_t* frames_host, int n
   const size_t fbytes = gbytes * channels;
   *total_host = 0;
   if (n == 0) return DCU_OK;
+  if (e->use_graphs && channels == 1 && n <= e->graph_max_n && n <= e->mb1 && !e->profiling && (!use_refinenet || e->has_ref)) {
+    const int rc = infer_small_graph(e, frames_host, n, dust_bin_ids, use_refinenet, counts_host, offsets_host, total_host, kpts_host,
+                                     refined_host, s);
+    if (rc != 1) return rc;
+  }
   if (channels == 3 && e->bgr.p == nullptr) CK(e->bgr.alloc((size_t)e->cfg.max_batch * e->cfg.height * e->cfg.width * 3));
   // stage through the engine's pinned buffer unless the caller's memory is already pinned (BGR: pageable copies are used as is)
   const uint8_t* src = frames_host;

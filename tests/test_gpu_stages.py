@@ -172,6 +172,35 @@ def test_refinenet_on_reference_patches(engine, golden_synth):
     assert np.array_equal(got, oracle.bargmax2d(heat.cpu().numpy()))
 
 
+def test_refinenet_16384_patches_periodic(states, golden_synth):
+    """BASELINE config 4 size (16384 patches, four chunks of 4096): the golden patches cycled.  A patch's result may not depend on
+    its position in the batch (flat pixel runs put patches at every offset inside the 128-pixel MMA tiles), so the output is
+    periodic and equal to the small-batch result; refined = kp + (corner - 32) / 8 exactly."""
+    g = golden_synth
+    p0 = g["patches"].shape[0]
+    e = N.Engine(states[0], states[1], 240, 320, 16, 0, max_batch=16, max_patches=16384)
+    try:
+        reps = (16384 + p0 - 1) // p0
+        patches = _cuda(np.tile(g["patches"], (reps, 1, 1))[:16384])
+        kp = _cuda(np.tile(g["kpts"][:p0].astype(np.int32), (reps, 1))[:16384])
+        corners = torch.empty((16384, 2), dtype=torch.int32, device="cuda")
+        refined = torch.empty((16384, 2), device="cuda")
+        N.check(N.lib().dcu_refine_forward(e.handle, patches.data_ptr(), kp.data_ptr(), 2, 16384, corners.data_ptr(),
+                                           refined.data_ptr(), None, None))
+        small_c = torch.empty((p0, 2), dtype=torch.int32, device="cuda")
+        small_r = torch.empty((p0, 2), device="cuda")
+        N.check(N.lib().dcu_refine_forward(e.handle, patches.data_ptr(), kp.data_ptr(), 2, p0, small_c.data_ptr(),
+                                           small_r.data_ptr(), None, None))
+        torch.cuda.synchronize()
+        c, r = corners.cpu().numpy(), refined.cpu().numpy()
+        idx = np.arange(16384) % p0
+        assert np.array_equal(c, small_c.cpu().numpy()[idx]) and np.array_equal(r, small_r.cpu().numpy()[idx])
+        assert np.array_equal(r, (c.astype(np.float32) - 32) / 8 + kp.cpu().numpy().astype(np.float32))
+        assert (c != g["corners"][:p0][idx]).any(1).sum() <= reps          # at most the one near-tie of the golden set, repeated
+    finally:
+        e.close()
+
+
 def _layer(engine, net, layer, impl, x, out_shape):
     n, c, h, w = x.shape
     xin = _cuda(x)
