@@ -286,7 +286,7 @@ def main():
                           decode_gather=dict(bound="hbm", achieved=(dec_bytes / (dec_ms / 1e3) / 1e9) if dec_ms > 0 else 0.0,
                                              peak=peaks["hbm"], unit="GB/s", launches=int(dec_n), kernel_ms_per_step=dec_ms / 2)),
         )
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (the other ranks would be spinning on the barrier)
             fps, cores, done, dt = cpu_reference_fps(pool[:32], seconds_budget=15.0)
             line["cpu_baseline"] = dict(value=fps, unit=UNIT, cores=cores, kind="port",
                                         sample=f"{done} frames of the same synthetic set in {dt:.1f} s, one frame per call "

@@ -319,6 +319,7 @@ struct DcuEngine {
   cudaStream_t gstream = nullptr;       // capture stream
   bool use_graphs = true;               // DCU_GRAPH=0: always launch kernel by kernel
   int graph_max_n = 8;
+  int graph_hint = 0;                   // recent corner count per call, picks the graph's number of patch slots
   // optional per-launch event timing (dcu_profile_*)
   struct ProfRec { cudaEvent_t a, b; double work; int cls; int shape[5]; double issued; };   // shape: cin, cout, hout, wout, n
   bool profiling = false;
@@ -1088,10 +1089,14 @@ static int infer_small_graph(DcuEngine* e, const uint8_t* frames_host, int n, in
                              int32_t* counts_host, int32_t* offsets_host, int32_t* total_host, int32_t* kpts_host,
                              float* refined_host, cudaStream_t s) {
   const int H = e->cfg.height, W = e->cfg.width;
-  const int pfix = std::min(32 * n, e->cfg.max_patches);
+  // patch slots: the smallest of 8 / 16 / 32 per frame that held the corner counts of the recent calls (video frames are alike);
+  // a frame with more corners than slots finishes kernel by kernel below and widens the hint
+  int per = 8;
+  while (per < 32 && per * n < e->graph_hint) per *= 2;
+  const int pfix = std::min(per * n, e->cfg.max_patches);
   DcuEngine::SmallGraph* g = nullptr;
   for (auto& x : e->graphs)
-    if (x.n == n && x.dust == dust_bin_ids && x.use_ref == use_refinenet) g = &x;
+    if (x.n == n && x.dust == dust_bin_ids && x.use_ref == use_refinenet && x.pfix == pfix) g = &x;
   if (!g) {            // first call of this shape runs kernel by kernel (sets function attributes, allocates lazily)
     if (e->graphs.size() >= 64) return 1;
     DcuEngine::SmallGraph x; x.n = n; x.dust = dust_bin_ids; x.use_ref = use_refinenet; x.pfix = pfix;
@@ -1140,6 +1145,8 @@ static int infer_small_graph(DcuEngine* e, const uint8_t* frames_host, int n, in
   CK(cudaStreamSynchronize(s));
   const int total = e->h_total[0];
   const int kept = std::min(total, e->cfg.max_patches);
+  // hint = recent maximum: jumps up at once, decays slowly (1/16 per call)
+  e->graph_hint = std::max(total, e->graph_hint - std::max(1, e->graph_hint / 16));
   if (total > g->pfix) {
     // crowded frames: more corners than the graph's patch slots -> finish kernel by kernel on the device-resident decode output
     if (use_refinenet) {
