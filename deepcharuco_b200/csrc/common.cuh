@@ -166,6 +166,15 @@ struct PnpParams {
 };
 void launch_pnp_batch(const PnpParams& q, const double* camera9, const double* dist, int n_dist, cudaStream_t s);
 
+// detector validation metric (metrics.cu): per-sample distance / match ratio of the decode output against label maps
+struct MetricsParams {
+  const int32_t* counts; const int32_t* offsets; const int32_t* kpts;
+  const long long* loc_target; const long long* ids_target;     // [n][h][w] int64, as the reference's dataset yields them
+  int n, h, w, dust_bin;
+  float* l2; float* ratio; int32_t* valid;                      // [n]
+};
+void launch_dc_metrics(const MetricsParams& p, cudaStream_t s);
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace dcu

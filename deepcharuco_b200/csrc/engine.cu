@@ -1239,6 +1239,24 @@ static int infer_batch_host_impl(DcuEngine* e, const uint8_t* frames_host, int n
   return DCU_OK;
 }
 
+int dcu_dc_metrics(DcuEngine* e, const int32_t* counts_dev, const int32_t* offsets_dev, const int32_t* kpts_dev, int n,
+                   const int64_t* loc_target_dev, const int64_t* ids_target_dev, int dust_bin_ids, float* l2_dev,
+                   float* ratio_dev, int32_t* valid_dev, void* stream) {
+  if (!e || !counts_dev || !offsets_dev || !kpts_dev || !loc_target_dev || !ids_target_dev || !l2_dev || !ratio_dev || !valid_dev || n < 0)
+    return fail(DCU_ERR_INVALID, "dcu_dc_metrics: bad argument");
+  if (dust_bin_ids < 0 || dust_bin_ids > 63) return fail(DCU_ERR_INVALID, "dcu_dc_metrics: ids above 63 are not supported");
+  CK(cudaSetDevice(e->cfg.device));
+  MetricsParams p{};
+  p.counts = counts_dev; p.offsets = offsets_dev; p.kpts = kpts_dev;
+  p.loc_target = reinterpret_cast<const long long*>(loc_target_dev); p.ids_target = reinterpret_cast<const long long*>(ids_target_dev);
+  p.n = n; p.h = e->cfg.height / 8; p.w = e->cfg.width / 8; p.dust_bin = dust_bin_ids;
+  p.l2 = l2_dev; p.ratio = ratio_dev; p.valid = valid_dev;
+  launch_dc_metrics(p, (cudaStream_t)stream);
+  if (n > 0) e->launches++;
+  CK(cudaGetLastError());
+  return DCU_OK;
+}
+
 // ---- batched solve_pnp (inference.py:15-29) ----
 static int pnp_object_table(DcuEngine* e, int col_count, int row_count, double square_len) {
   // object_points[:, :2] = meshgrid(arange(1,row_count), arange(1,col_count)).reshape(2,-1).T * square_len  (float32 storage):

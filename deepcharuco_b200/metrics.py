@@ -1,0 +1,80 @@
+"""Detector validation metric at engine speed.
+
+`DC_Metrics` mirrors /root/reference/src/models/metrics.py:38-146 (same constructor argument, `update(preds, target)`,
+`compute()`, same accumulation), but the per-sample work -- decode of the logits, label decode, per-id worst distance and
+match ratio -- runs in two kernels on the B200 (`dcu_decode_gather`, `dcu_dc_metrics`) instead of a Python loop over samples.
+`update_frames` feeds uint8 frames through the engine's own detector first (what a validation loop over images does)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+class DC_Metrics:
+    higher_is_better = False
+
+    def __init__(self, dust_bin_ids, deepc):
+        """deepc: a model handle from load_models (selects device and weights).  metrics.py:42-47."""
+        self.dust_bin_ids = int(dust_bin_ids)
+        self.px_margin = 3
+        self._ctx = deepc._ctx
+        self.distance = np.float32(0.0)
+        self.ratio = np.float32(0.0)
+
+    def _accumulate(self, l2, ratio, valid, bs):
+        # metrics.py:56-73: sums over the samples that have labels, divided by the batch size
+        if valid.any():
+            self.distance = np.float32(self.distance + np.float32(l2[valid].sum(dtype=np.float32)) / np.float32(bs))
+            self.ratio = np.float32(self.ratio + np.float32(ratio[valid].sum(dtype=np.float32)) / np.float32(bs))
+
+    def _metrics(self, eng, counts, offsets, kpts, n, target):
+        import torch
+        loc_t, ids_t = target
+        dev = counts.device
+        loc_t = torch.as_tensor(loc_t).to(device=dev, dtype=torch.int64).contiguous()
+        ids_t = torch.as_tensor(ids_t).to(device=dev, dtype=torch.int64).contiguous()
+        assert loc_t.shape == ids_t.shape == (n, eng.height // 8, eng.width // 8), "labels must be (N, H/8, W/8)"
+        l2 = torch.empty(n, dtype=torch.float32, device=dev)
+        ratio = torch.empty(n, dtype=torch.float32, device=dev)
+        valid = torch.empty(n, dtype=torch.int32, device=dev)
+        s = torch.cuda.current_stream(dev).cuda_stream
+        N.check(N.lib().dcu_dc_metrics(eng.handle, counts.data_ptr(), offsets.data_ptr(), kpts.data_ptr(), n, loc_t.data_ptr(),
+                                       ids_t.data_ptr(), self.dust_bin_ids, l2.data_ptr(), ratio.data_ptr(), valid.data_ptr(), s))
+        l2, ratio, valid = l2.cpu().numpy(), ratio.cpu().numpy(), valid.cpu().numpy().astype(bool)
+        self._accumulate(l2, ratio, valid, n)
+        return l2, ratio, valid
+
+    def update(self, preds, target):
+        """preds = (loc_hat (N,65,h,w), ids_hat (N,n_ids+1,h,w)) float32 CUDA tensors, target = (loc (N,h,w), ids (N,h,w)) integer
+        label maps -- metrics.py:49-51.  Returns the per-sample (l2, ratio, valid) arrays as a convenience."""
+        import torch
+        loc_x, ids_x = preds
+        n, _, h, w = loc_x.shape
+        eng = self._ctx.engine(8 * h, 8 * w, max_batch=n)
+        dev = torch.device("cuda", eng.device)
+        loc_x = loc_x.to(device=dev, dtype=torch.float32).contiguous()
+        ids_x = ids_x.to(device=dev, dtype=torch.float32).contiguous()
+        counts = torch.empty(n, dtype=torch.int32, device=dev)
+        offsets = torch.empty(n, dtype=torch.int32, device=dev)
+        total = torch.zeros(1, dtype=torch.int32, device=dev)
+        kpts = torch.empty((eng.max_patches, 4), dtype=torch.int32, device=dev)
+        s = torch.cuda.current_stream(dev).cuda_stream
+        N.check(N.lib().dcu_decode_gather(eng.handle, loc_x.data_ptr(), ids_x.data_ptr(), None, n, self.dust_bin_ids, 0,
+                                          counts.data_ptr(), offsets.data_ptr(), total.data_ptr(), kpts.data_ptr(), None, s))
+        return self._metrics(eng, counts, offsets, kpts, n, target)
+
+    def update_frames(self, frames_u8, target):
+        """frames (N,H,W) uint8 -> the engine's detector + decode (no RefineNet) -> the same metric update."""
+        import torch
+        frames = np.ascontiguousarray(frames_u8, np.uint8)
+        n, H, W = frames.shape
+        eng = self._ctx.engine(H, W, max_batch=n)
+        dev = torch.device("cuda", eng.device)
+        fr = torch.from_numpy(frames).to(dev)
+        o = eng.infer_batch_device(fr.data_ptr(), n, self.dust_bin_ids, False, torch.cuda.current_stream(dev).cuda_stream)
+        return self._metrics(eng, o["counts"], o["offsets"], o["kpts"], n, target)
+
+    def compute(self):
+        """metrics.py:131-132."""
+        return self.distance, self.ratio

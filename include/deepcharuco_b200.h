@@ -174,6 +174,16 @@ int dcu_solve_pnp_batch_host(DcuEngine* e, const int32_t* counts_host, const int
                              const double* dist_coeffs, int n_dist, int32_t* ret_host, double* rvec_host, double* tvec_host,
                              void* stream);
 
+/* Detector validation metric on the device: the per-sample part of DC_Metrics.update (models/metrics.py:48-73, i.e.
+ * compute_l2_distance :102-129 and compute_ratio :75-100) on the decode output of dcu_decode_gather / dcu_infer_batch
+ * (counts / offsets / kpts) against the label maps loc_target / ids_target [n][H/8][W/8] int64 (the reference dataset's
+ * label format, decoded like label_to_keypoints :25-35).  Per sample: l2[f] = mean over matched label ids of the worst
+ * prediction-to-label distance in pixels, ratio[f] = share of labels matched within 3 px, valid[f] = 0 when the sample
+ * has no labels (the reference skips it).  The caller accumulates like DC_Metrics: distance += sum(l2[valid]) / n. */
+int dcu_dc_metrics(DcuEngine* e, const int32_t* counts_dev, const int32_t* offsets_dev, const int32_t* kpts_dev, int n,
+                   const int64_t* loc_target_dev, const int64_t* ids_target_dev, int dust_bin_ids, float* l2_dev,
+                   float* ratio_dev, int32_t* valid_dev, void* stream);
+
 /* Select the 3x3 conv implementation after creation (DCU_CONV_*). */
 int dcu_set_conv_impl(DcuEngine* e, int conv_impl);
 

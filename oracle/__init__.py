@@ -24,3 +24,4 @@ from .decode import (pre_bgr_image, pred_argmax, label_to_keypoints,  # noqa: F4
                      pred_to_keypoints, extract_patches, bargmax2d,
                      refine_corners, marshal_keypoints)
 from .pipeline import infer_image, infer_gray_batch, solve_pnp  # noqa: F401
+from . import metrics  # noqa: F401

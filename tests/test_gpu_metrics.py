@@ -1,0 +1,52 @@
+"""DC_Metrics on the device against the reference's own DC_Metrics outputs
+(tests/golden/metrics_seed0.npz) and the oracle restatement, through dcu_decode_gather + dcu_dc_metrics."""
+import numpy as np
+import pytest
+import torch
+
+import deepcharuco_b200 as dc
+import oracle
+from conftest import load_golden
+from deepcharuco_b200.metrics import DC_Metrics
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6      # fp32: per-id distances are bit-exact (integer coordinates); only the order of the final sums differs
+
+
+@pytest.fixture(scope="module")
+def models():
+    return dc.load_models(dc.DEFAULT_DEEPC, dc.DEFAULT_REFINENET, n_ids=16, device="cuda")
+
+
+def _one_hot(arg, c):
+    return torch.from_numpy((np.arange(c)[None, :, None, None] == arg[:, None]).astype(np.float32)).cuda()
+
+
+def test_update_on_logits_matches_reference(models):
+    g = load_golden("metrics_seed0.npz")
+    m = DC_Metrics(16, models[0])
+    loc_hat, ids_hat = _one_hot(g["loc_argmax"], 65), _one_hot(g["ids_argmax"], 17)
+    l2, ratio, valid = m.update((loc_hat, ids_hat), (g["loc_target"], g["ids_target"]))
+    want_valid = ~np.isnan(g["per_l2"])
+    assert np.array_equal(valid, want_valid)
+    assert np.allclose(l2[valid], g["per_l2"][want_valid], rtol=TOL, atol=TOL) and np.allclose(ratio[valid], g["per_ratio"][want_valid], rtol=TOL, atol=TOL)
+    assert np.allclose(m.compute(), g["after_update1"], rtol=TOL, atol=TOL)
+    m.update((loc_hat[3:8], ids_hat[3:8]), (g["loc_target"][3:8], g["ids_target"][3:8]))
+    assert np.allclose(m.compute(), g["after_update2"], rtol=TOL, atol=TOL)
+
+
+def test_update_frames_end_to_end(models, golden_synth):
+    """Frames -> the engine's detector + decode -> metric: equals the reference's metric on the reference's logits, because the
+    engine's kept cells / ids / pixels are bit-exact."""
+    g = load_golden("metrics_seed0.npz")
+    m = DC_Metrics(16, models[0])
+    l2, ratio, valid = m.update_frames(golden_synth["frames"], (g["loc_target"], g["ids_target"]))
+    want_valid = ~np.isnan(g["per_l2"])
+    assert np.array_equal(valid, want_valid)
+    assert np.allclose(l2[valid], g["per_l2"][want_valid], rtol=TOL, atol=TOL)
+    assert np.allclose(ratio[valid], g["per_ratio"][want_valid], rtol=TOL, atol=TOL)
+    assert np.allclose(m.compute(), g["after_update1"], rtol=TOL, atol=TOL)
+    # and the oracle on the same inputs
+    o = oracle.metrics.DCMetrics(16)
+    o.update((_one_hot(g["loc_argmax"], 65).cpu().numpy(), _one_hot(g["ids_argmax"], 17).cpu().numpy()), (g["loc_target"], g["ids_target"]))
+    assert np.allclose(m.compute(), o.compute(), rtol=TOL, atol=TOL)

@@ -1,0 +1,26 @@
+"""oracle/metrics.py against the outputs of the reference's own DC_Metrics (tests/golden/metrics_seed0.npz,
+tools/make_golden_metrics.py).  Predictions enter as the reference's arg-max maps (one-hot logits give the same decode)."""
+import numpy as np
+
+import oracle
+from conftest import load_golden
+
+
+def _one_hot(arg, c):
+    return (np.arange(c)[None, :, None, None] == arg[:, None]).astype(np.float32)
+
+
+def test_metrics_oracle_matches_reference():
+    g = load_golden("metrics_seed0.npz")
+    loc_hat, ids_hat = _one_hot(g["loc_argmax"], 65), _one_hot(g["ids_argmax"], 17)
+    m = oracle.metrics.DCMetrics(16)
+    for i in range(loc_hat.shape[0]):
+        l2, ratio = m.sample(loc_hat[i], ids_hat[i], g["loc_target"][i], g["ids_target"][i])
+        if np.isnan(g["per_l2"][i]):
+            assert l2 is None and ratio is None            # a sample without labels (metrics.py:80-81, :106-107)
+        else:
+            assert abs(l2 - g["per_l2"][i]) <= 1e-6 * max(1.0, g["per_l2"][i]) and abs(ratio - g["per_ratio"][i]) <= 1e-6
+    m.update((loc_hat, ids_hat), (g["loc_target"], g["ids_target"]))
+    assert np.allclose(m.compute(), g["after_update1"], rtol=1e-6, atol=1e-6)
+    m.update((loc_hat[3:8], ids_hat[3:8]), (g["loc_target"][3:8], g["ids_target"][3:8]))
+    assert np.allclose(m.compute(), g["after_update2"], rtol=1e-6, atol=1e-6)
