@@ -742,6 +742,7 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   DcuEngine* e = new DcuEngine();
   e->cfg = *cfg;
   e->sm_count = prop.multiProcessorCount;
+  if (const char* v = getenv("DCU_SMS")) e->sm_count = std::max(2, std::min(atoi(v), prop.multiProcessorCount));   // experiments
   e->conv_impl = cfg->conv_impl;
   int rc;
 #define TRY(x) do { if ((rc = (x)) != DCU_OK) { delete e; return rc; } } while (0)

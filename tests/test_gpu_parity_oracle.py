@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import deepcharuco_b200 as dc
-from deepcharuco_b200 import synth
+from deepcharuco_b200 import synth, _native as N
 import parity
 
 pytestmark = pytest.mark.gpu
@@ -31,6 +31,35 @@ def test_parity_640x480(models, states):
     tot = parity.summarise([parity.compare_frame(states, f, r, w) for f, r, w in zip(frames, refined, raw)])
     print("PARITY 640x480 seed5:", tot)
     parity.assert_parity(tot)
+
+
+@pytest.mark.parametrize("hw", [(200, 296), (24, 24), (136, 72)])
+def test_parity_awkward_sizes(models, states, hw):
+    """Frame sizes that are multiples of 8 but of nothing else the kernels tile by: odd cell grids (25 x 37, 3 x 3, 17 x 9), maps whose
+    pooled sizes are odd, tiles that overhang on every edge; 24 x 24 is the smallest frame the engine accepts."""
+    deepc, refinenet = models
+    H, W = hw
+    big = synth.make_frames(6, 240, 320, seed=9)
+    frames = np.ascontiguousarray(big[:, 20:20 + H, 12:12 + W])
+    refined = dc.infer_batch(frames, 16, deepc, refinenet)
+    raw = dc.infer_batch(frames, 16, deepc, None)
+    tot = parity.summarise([parity.compare_frame(states, f, r, w) for f, r, w in zip(frames, refined, raw)])
+    print("PARITY %dx%d:" % (W, H), tot)
+    parity.assert_parity(tot)
+    # small crops rarely keep a corner, so also compare what the detector itself produces at this size
+    import torch
+    import oracle
+    eng = deepc._ctx.engine(H, W, max_batch=len(frames))
+    fr = torch.from_numpy(frames).cuda()
+    loc = torch.empty((len(frames), 65, H // 8, W // 8), device="cuda")
+    ids = torch.empty((len(frames), 17, H // 8, W // 8), device="cuda")
+    N.check(N.lib().dcu_detector_forward(eng.handle, fr.data_ptr(), len(frames), loc.data_ptr(), ids.data_ptr(), None))
+    torch.cuda.synchronize()
+    x = torch.from_numpy(np.stack([oracle.pre_bgr_image(f) for f in frames]))
+    wl, wi = oracle.detector_forward(states[0], x)
+    wl, wi = wl.numpy(), wi.numpy()
+    assert np.abs(loc.cpu().numpy() - wl).max() < 0.25 and np.abs(ids.cpu().numpy() - wi).max() < 0.25     # logits are O(100)
+    assert np.array_equal(ids.cpu().numpy().argmax(1), wi.argmax(1))
 
 
 def test_properties_at_batch_256(models):

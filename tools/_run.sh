@@ -1,2 +1,1 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 20 --warmup 5 2>gpurun_out/r1c_2gpu.err | tail -1 > gpurun_out/r1c_bench_2gpu.json; cat gpurun_out/r1c_bench_2gpu.json | cut -c1-600; tail -3 gpurun_out/r1c_2gpu.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>/dev/null | tail -1 | cut -c1-300
+(timeout 600 python -m pytest tests/test_gpu_parity_oracle.py -m gpu -x -q -k awkward -s 2>&1 | tail -15)
