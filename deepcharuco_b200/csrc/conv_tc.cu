@@ -539,11 +539,13 @@ template <int NT, int KS>
 static cudaError_t launch_nt(const ConvParams& p, const float* w_blocks, int n_slices, int w_copies, const CUtensorMap* tm,
                              int sm_count, cudaStream_t s) {
   using Cfg = TcCfg<NT>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};      // function attributes are per device: engines on several GPUs of one process each opt in
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<NT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   TcGeo g;
   tc_tile_arrangement(NT, p.hout, p.wout, &g.tr, &g.tc);

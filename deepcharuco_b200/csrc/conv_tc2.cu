@@ -525,11 +525,13 @@ template <int NT, int KS, bool UP, bool WRES = false>
 cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta, const CUtensorMap* w0, const CUtensorMap* w1,
                         int sm_count, cudaStream_t s, double* issued_flops) {
   using Cfg = Tc2Cfg<NT, UP, WRES>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};      // function attributes are per device: engines on several GPUs of one process each opt in
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NT, KS, UP, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   Tc2Geo g{};
   if (UP && (p.pad != 1 || p.pool || p.ups || p.hout != 2 * p.hin || p.wout != 2 * p.win)) return cudaErrorInvalidValue;
