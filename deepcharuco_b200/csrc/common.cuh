@@ -69,8 +69,13 @@ struct ConvParams {
   H2Layout out_layout;
   int flat_in, in_period, in_row;
   const struct TcBn* host_bn;   // host copy of bias / alpha / beta: the pair kernel takes them by value (constant bank)
+  // FIRST mode of the pair kernel: `in` is unused; the 64 input channels are conv1a (+BN+ReLU) of the frames, computed in-kernel
+  const struct FirstWeights* first_w;   // host copy of conv1a's weights / BN constants, or null
+  const uint8_t* first_u8;              // [n][hin][win] u8 frames (normalised in-kernel), or
+  const float* first_f32;               // [n][hin][win] already normalised images
 };
 struct TcBn { float v[3][512]; };   // [bias | alpha | beta][channel]
+struct FirstWeights { float w[9 * 64]; float bias[64], alpha[64], beta[64]; };   // conv1a: w[tap][channel], BN as y = fma(acc + bias, alpha, beta)
 
 // FFMA path: weights packed [cin/4][9 taps][4 cin][cout_total] with the cout axis permuted per 64-block
 // so a thread's 8 channels are two float4 that are bank-conflict free (see conv_ffma.cu).

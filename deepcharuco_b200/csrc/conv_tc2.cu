@@ -20,6 +20,15 @@
 //     fire in both CTAs, so each CTA's producers and epilogue wait on their local copy;
 //   * acc_empty lives in the leader and counts the epilogue threads of BOTH CTAs (remote mbarrier.arrive via mapa).
 //
+// FIRST mode (ConvParams::first_w): the detector's conv1a (1 -> 64, net.py:60) is computed INSIDE conv1b's kernel.  conv1a's output
+// is 19.7 MB per frame; written by its own kernel and read back by conv1b it was 10 GB of HBM traffic per 256-frame step and a
+// write-bound 1.5 ms kernel (10 % of the step).  Here six producer warps per CTA (warps 8-11, 0 and 3; the epilogue, fully overlapped
+// for NT = 64, shrinks to warps 4-7) read the u8 frame window of the tile (+2 pixels), evaluate conv1a + BN + ReLU on the CUDA cores
+// with the same FMA order as conv_first_kernel (bit-identical values), split to fp16 hi/lo and store the halo tile straight into
+// the A stage in the layout the TMA box would have produced, 16 channels per stage.  Weights and BN constants are constant-bank
+// operands (by-value parameter).  generic-proxy stores -> fence.proxy.async -> release.cluster arrive on the leader's a_full
+// (count 12 = 6 warps x 2 CTAs); conv1b's zero padding = zeros for halo pixels outside the image.
+//
 // FLAT mode (ConvParams::flat_in, F2 tensors of common.cuh).  RefineNet's first maps are 22x22 ... 8x8 pixels: a 16x8 /
 // 16x16 pixel tile of such a map is mostly empty (8x8: 25 % of the MMA rows useful).  In FLAT mode all images of the launch
 // form ONE run of pixels j = k*period + y*row + x, an m-tile is 128 CONSECUTIVE pixels of that run and a tap (ky, kx) is the
@@ -32,6 +41,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -58,7 +68,9 @@ struct Tc2Cfg {
   static constexpr int B_BLOCK_BYTES = B_MAIN_BYTES + B_X_BYTES;   // 48 * NT
   static constexpr int B_STAGE_BYTES = STAGE_BLOCKS * B_BLOCK_BYTES;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int WIN_ELEMS = 36 * 12;                        // FIRST: input window (halo + 2) of the largest tile arrangement
+  static constexpr int WIN_BYTES = 2 * WIN_ELEMS * 4 + 768 * 4;    // two windows (double-buffered) + conv1a's weight / BN table, fp32
+  static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + BAR_BYTES + WIN_BYTES + 1024;
 };
 
 struct Tc2Geo {
@@ -89,6 +101,35 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
+}
+// release at cluster scope: publishes this thread's (fenced) shared-memory stores to the waiter in the leader CTA
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 remAddr32;\n"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remAddr32];\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity))
+    if (clock64() - t0 > 4000000000LL) __trap();
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -205,6 +246,13 @@ __device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint3
   hi = *reinterpret_cast<const uint32_t*>(&hh);
   lo = *reinterpret_cast<const uint32_t*>(&ll);
 }
+__device__ __forceinline__ void split_h2_noclamp(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 hh = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
 __device__ __forceinline__ void store_h2_16(uint4* hi_plane0, size_t lo_offset, size_t kg_stride, const float* v) {
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
@@ -236,10 +284,12 @@ __device__ __forceinline__ Tile2 decode_pair_tile(long long pt, uint32_t rank, c
   return c;
 }
 
-template <int NT, int KS, bool UP, bool WRES>
+struct NoFirst {};
+template <int NT, int KS, bool UP, bool WRES, bool FIRST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w0,
-                const __grid_constant__ CUtensorMap tmap_w1, const ConvParams p, const Tc2Geo g, const __grid_constant__ TcBn bn) {
+                const __grid_constant__ CUtensorMap tmap_w1, const ConvParams p, const Tc2Geo g, const __grid_constant__ TcBn bn,
+                const __grid_constant__ typename std::conditional<FIRST, FirstWeights, NoFirst>::type fw) {
   // bn: bias / BN scale / BN shift by value = constant bank.  The epilogue's channel index is warp-uniform, so these become
   // uniform constant loads instead of shared-memory reads (the shared-memory data pipe is what bounds this kernel).
   using Cfg = Tc2Cfg<NT, UP, WRES>;
@@ -259,6 +309,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t* acc_full = b_empty + B_STAGES;
   uint64_t* acc_empty = acc_full + NBUF;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NBUF * MT);
+  float* in_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);     // FIRST: input window of the tile
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -268,7 +319,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int halo_px = g.halo_w * g.halo_h;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < Cfg::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < Cfg::A_STAGES; ++i) { mbar_init(&a_full[i], FIRST ? 12 : 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < NBUF; ++i) mbar_init(&acc_full[i], 1);
     for (int i = 0; i < NBUF * MT; ++i) mbar_init(&acc_empty[i], 256);      // epilogue threads of both CTAs (leader's copy is used)
@@ -283,7 +334,131 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  if (FIRST && (warp >= 8 || warp == 0 || warp == 3)) {
+    // ================= conv1a producers (both CTAs): frame window -> conv1a + BN + ReLU -> hi/lo halo tile in the A stage =================
+    if constexpr (FIRST) {
+      // six producer warps: 8-11 plus the two that have no other role in this mode (0: no TMA activation loads, 3: spare)
+      const int pw = warp >= 8 ? warp - 8 : (warp == 0 ? 4 : 5);
+      const int ptid = pw * 32 + lane;
+      constexpr int PT = 192;
+      const int win_w = g.halo_w + 2, win_h = g.halo_h + 2;
+      int H = p.hin, W = p.win;
+      const uint8_t* f_u8 = p.first_u8;
+      const float* f_f32 = p.first_f32;
+      // keep these in registers: re-reading them from the parameter bank inside the tile loop missed the constant cache every time
+      // (the epilogue's 6 kB BN table shares it) -- 8 % of the producers' time on one LDCU
+      asm volatile("" : "+r"(H), "+r"(W), "+l"(f_u8), "+l"(f_f32));
+      // warp role: cg = which 8 of a chunk's 16 channels, pg = which half of the pixels; a thread's pixels (pg*32 + lane + 64k) are
+      // the same for every tile, so their (row, column) inside the halo is computed once
+      const int cg = pw & 1, pg = pw >> 1;
+      uint32_t hyx[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int px = pg * 32 + lane + 96 * k;
+        const int hy = px / g.halo_w;
+        hyx[k] = ((uint32_t)hy << 16) | (uint32_t)(px - hy * g.halo_w);
+      }
+      // conv1a's table in shared memory, channel-major per 8-channel group: [group][9 taps + bias, alpha, beta][8] -> 24 LDS.128 per
+      // (chunk, warp); indexed constant-bank loads (LDC) turned out to issue at ~1 per 15 cycles per SM and starved the producers
+      float* wtab = in_s + 2 * Cfg::WIN_ELEMS;
+      for (int i = ptid; i < 768; i += PT) {
+        const int grp8 = i / 96, r = (i - grp8 * 96) >> 3, j = i & 7, ch = grp8 * 8 + j;
+        wtab[i] = r < 9 ? fw.w[r * 64 + ch] : (r == 9 ? fw.bias[ch] : (r == 10 ? fw.alpha[ch] : fw.beta[ch]));
+      }
+      // the tile's frame window is fetched one tile ahead into registers (global latency hidden behind the previous tile's math)
+      const int win_n = win_w * win_h;
+      uint32_t pre[3];                                           // raw bits (u8 value or fp32 pattern): no arithmetic on them until they are used
+      auto prefetch = [&](long long pt) {
+        const Tile2 c = decode_pair_tile(pt, rank, g);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int i = ptid + PT * k;
+          const int iy = i / win_w, ix = i - iy * win_w;
+          const int gy = c.y0 - 2 + iy, gx = c.x0 - 2 + ix;
+          uint32_t v = 0xffffffffu;                              // marker: outside the image (a NaN pattern, never a normalised value)
+          if (i < win_n && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            const size_t o = ((size_t)c.img * H + gy) * W + gx;
+            v = f_u8 ? (uint32_t)f_u8[o] : __float_as_uint(f_f32[o]);
+          }
+          pre[k] = v;
+        }
+      };
+      prefetch(cluster_id);
+      int st = 0; uint32_t ph = 0, wb = 0;
+      for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
+        const Tile2 c = decode_pair_tile(pt, rank, g);
+        float* win = in_s + wb * Cfg::WIN_ELEMS;
+        wb ^= 1u;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int i = ptid + PT * k;
+          if (i < win_n) {
+            // conv1a's zero padding is applied to the NORMALISED image (net.py:23); (x - 128) / 255 as model_utils.py:48-49
+            const uint32_t v = pre[k];
+            win[i] = (v == 0xffffffffu) ? 0.f : (f_u8 ? __fdiv_rn((float)v - 128.0f, 255.0f) : __uint_as_float(v));
+          }
+        }
+        asm volatile("bar.sync 1, 192;" ::: "memory");          // window (and, first time, the table) visible to the six producer warps
+        if (pt + n_clusters < g.total_pairs) prefetch(pt + n_clusters);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          // this warp's 8 channels of the chunk: weights and BN constants into registers (FFMA operands), reused for all its pixels
+          float wr[9][8], cb[8], ca[8], ce[8];
+          {
+            const float4* tp = reinterpret_cast<const float4*>(wtab + (q * 2 + cg) * 96);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const float4 lo4 = tp[2 * t], hi4 = tp[2 * t + 1];
+              wr[t][0] = lo4.x; wr[t][1] = lo4.y; wr[t][2] = lo4.z; wr[t][3] = lo4.w;
+              wr[t][4] = hi4.x; wr[t][5] = hi4.y; wr[t][6] = hi4.z; wr[t][7] = hi4.w;
+            }
+            const float4 b0 = tp[18], b1 = tp[19], a0 = tp[20], a1 = tp[21], e0 = tp[22], e1 = tp[23];
+            cb[0] = b0.x; cb[1] = b0.y; cb[2] = b0.z; cb[3] = b0.w; cb[4] = b1.x; cb[5] = b1.y; cb[6] = b1.z; cb[7] = b1.w;
+            ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
+            ce[0] = e0.x; ce[1] = e0.y; ce[2] = e0.z; ce[3] = e0.w; ce[4] = e1.x; ce[5] = e1.y; ce[6] = e1.z; ce[7] = e1.w;
+          }
+          mbar_wait<40>(&a_empty[st], ph ^ 1u);
+          uint4* stage = reinterpret_cast<uint4*>(a_smem + (size_t)st * Cfg::A_STAGE_BYTES) + cg * halo_px;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int px = pg * 32 + lane + 96 * k;
+            if (px >= halo_px) continue;
+            const int hy = (int)(hyx[k] >> 16), hx = (int)(hyx[k] & 0xffffu);
+            const int gy = c.y0 - 1 + hy, gx = c.x0 - 1 + hx;
+            if (!(gy >= 0 && gy < H && gx >= 0 && gx < W)) {                 // outside the image: conv1b's own zero padding
+              stage[px] = make_uint4(0u, 0u, 0u, 0u);
+              stage[2 * halo_px + px] = make_uint4(0u, 0u, 0u, 0u);
+              continue;
+            }
+            const float* ip = win + hy * win_w + hx;
+            float v[9];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) v[ky * 3 + kx] = ip[ky * win_w + kx];
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t)                                                // taps ascending from 0: conv_first_kernel's order;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y[j] = fmaf(v[t], wr[t][j], y[j]);           // 8 independent chains interleaved
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = fmaxf(fmaf(y[j] + cb[j], ca[j], ce[j]), 0.0f);
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_h2_noclamp(y[2 * e], y[2 * e + 1], h[e], l[e]);   // |conv1a| < 65504 is checked on the host
+            stage[px] = make_uint4(h[0], h[1], h[2], h[3]);                            // hi plane of this k-group
+            stage[2 * halo_px + px] = make_uint4(l[0], l[1], l[2], l[3]);              // lo plane
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                 // generic-proxy stores -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&a_full[st], 0);     // release (default) after the proxy fence, as cutlass' producer_commit
+          if (++st == Cfg::A_STAGES) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (!FIRST && warp == 0 && lane == 0) {
     // ================= activation producer: this CTA's halo into this CTA's smem, bytes credited to the leader =================
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
     int st = 0; uint32_t ph = 0;
@@ -382,10 +557,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       if (++buf == NBUF) { buf = 0; phc ^= 1u; }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && (!FIRST || warp < 8)) {
     // ================= epilogue (both CTAs, each drains its own 128 TMEM lanes) =================
     constexpr int CW = 16;
-    const int grp = (warp >= 8) ? 1 : 0;
+    const int grp = (!FIRST && warp >= 8) ? 1 : 0;       // FIRST: warps 4-7 drain both m-tiles (warps 8-11 are the conv1a producers)
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;
     const int prow = m >> 3, pcol = m & 7;
@@ -399,7 +574,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       tc_fence_after();
       const int ch_base = (UP ? (c.slice >> 1) : c.slice) * NT;
 #pragma unroll 1
-      for (int mt = grp; mt < MT; mt += 2) {
+      for (int mt = grp; mt < MT; mt += (FIRST ? 1 : 2)) {
         int oy, ox, img = c.img;
         bool inb;
         if (g.flat) {    // pixel j of the run -> (image, y, x) by the input's period / row stride; wrap-around positions are dropped
@@ -521,7 +696,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
-template <int NT, int KS, bool UP, bool WRES = false>
+template <int NT, int KS, bool UP, bool WRES = false, bool FIRST = false>
 cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta, const CUtensorMap* w0, const CUtensorMap* w1,
                         int sm_count, cudaStream_t s, double* issued_flops) {
   using Cfg = Tc2Cfg<NT, UP, WRES>;
@@ -529,7 +704,7 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NT, KS, UP, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NT, KS, UP, WRES, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
@@ -574,7 +749,14 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
   if (issued_flops) *issued_flops = 2.0 * (double)g.total_pairs * (p.cin / 16) * (UP ? 4 : KS * KS) * Cfg::MT * 256.0 * 3.0 * NT * 16.0;
   const long long clusters = g.total_pairs < sm_count / 2 ? g.total_pairs : sm_count / 2;
   if (p.host_bn == nullptr) return cudaErrorInvalidValue;
-  conv_tc2_kernel<NT, KS, UP, WRES><<<(int)clusters * 2, T2_THREADS, Cfg::SMEM_BYTES, s>>>(*ta, *w0, *w1, p, g, *p.host_bn);
+  if constexpr (FIRST) {
+    if (p.first_w == nullptr || (!p.first_u8 && !p.first_f32) || p.cin != 64 || p.pad != 1 || g.flat ||
+        (g.halo_w + 2) * (g.halo_h + 2) > Cfg::WIN_ELEMS || (g.halo_w + 2) * (g.halo_h + 2) > 576 || g.halo_w * g.halo_h > 384)
+      return cudaErrorInvalidValue;
+    conv_tc2_kernel<NT, KS, UP, WRES, true><<<(int)clusters * 2, T2_THREADS, Cfg::SMEM_BYTES, s>>>(*ta, *w0, *w1, p, g, *p.host_bn, *p.first_w);
+  } else {
+    conv_tc2_kernel<NT, KS, UP, WRES, false><<<(int)clusters * 2, T2_THREADS, Cfg::SMEM_BYTES, s>>>(*ta, *w0, *w1, p, g, *p.host_bn, NoFirst());
+  }
   return cudaGetLastError();
 }
 
@@ -600,6 +782,11 @@ cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const voi
     return cudaErrorInvalidValue;
   }
   static const bool wres_ok = [] { const char* v = getenv("DCU_WRES"); return !v || atoi(v) != 0; }();
+  if (p.first_w != nullptr) {
+    if (nt != 64 || n_slices != 1) return cudaErrorInvalidValue;
+    return wres_ok ? launch_pair<64, 3, false, true, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops)
+                   : launch_pair<64, 3, false, false, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+  }
   if (nt == 64 && n_slices == 1 && p.cin == 64 && wres_ok) return launch_pair<64, 3, false, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
   if (nt == 64) return launch_pair<64, 3, false>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
   if (nt == 128) return launch_pair<128, 3, false>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);

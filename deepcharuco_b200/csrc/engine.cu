@@ -63,6 +63,8 @@ struct Layer3x3 {
 
 struct FirstLayer {
   DevBuf w, bias, alpha, beta;   // [9][64], [64] x3
+  FirstWeights host{};           // the same values, passed by value to the fused conv1a + conv1b kernel (conv_tc2.cu FIRST mode)
+  float out_bound = 0.f;         // upper bound of |output| for inputs in [-0.51, 0.5] (the fused kernel splits to fp16 without a clamp)
   int pad = 1;
 };
 
@@ -298,6 +300,8 @@ struct DcuEngine {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_start = nullptr, ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   bool overlap_first = true;
+  bool f32_in_range = true;     // fp32 image inputs are normalised ((x-128)/255, |x| <= 0.51): required by the fused kernel's bound
+  bool fuse_first = true;       // detector: conv1a inside conv1b's kernel (DCU_FUSE_FIRST=0: separate conv1a kernel + HBM round trip)
   bool fuse_up = true;          // RefineNet: fold the 2x nearest upsamplings into the consuming convolution (DCU_FUSE_UP=0: materialise)
   bool flat = true;             // RefineNet maps up to conv4a's input as F2 runs (conv_tc2.cu FLAT mode; DCU_FLAT=0: per-patch tiles)
   DevBuf flat8[3];              // 8x8 maps in 9x9 cells (conv2b / conv3a / conv3b outputs); gutters stay zero
@@ -377,6 +381,15 @@ int build_first(FirstLayer& f, const DcuConvLayer& L, int pad) {
   for (int o = 0; o < 64; ++o)
     for (int t = 0; t < 9; ++t) w[t * 64 + o] = L.weight[o * 9 + t];
   f.pad = pad;
+  std::memcpy(f.host.w, w.data(), sizeof(f.host.w));
+  std::memcpy(f.host.bias, L.bias, 256); std::memcpy(f.host.alpha, L.alpha, 256); std::memcpy(f.host.beta, L.beta, 256);
+  f.out_bound = 0.f;
+  for (int o = 0; o < 64; ++o) {
+    double sw = 0;
+    for (int t = 0; t < 9; ++t) sw += std::fabs((double)L.weight[o * 9 + t]);
+    const double b = (0.51 * sw + std::fabs((double)L.bias[o])) * std::fabs((double)L.alpha[o]) + std::fabs((double)L.beta[o]);
+    f.out_bound = std::max(f.out_bound, (float)b);
+  }
   CK(upload(f.w, w));
   CK(upload(f.bias, std::vector<float>(L.bias, L.bias + 64)));
   CK(upload(f.alpha, std::vector<float>(L.alpha, L.alpha + 64)));
@@ -494,6 +507,7 @@ static int make_tmap_flat(CUtensorMap* tm, const void* base, long long px_used, 
   return DCU_OK;
 }
 
+struct FirstIn { const uint8_t* u8; const float* f32; const FirstWeights* w; };   // conv1a fused into this layer (conv_tc2.cu FIRST mode)
 struct FlatIn { int period, row; long long plane_px; };    // the layer's input is an F2 tensor (conv_tc2.cu FLAT mode)
 static long long flat_plane_px(int n, int period) { return (((long long)n * period + 15) / 16) * 16; }
 
@@ -505,9 +519,9 @@ static unsigned long long* g_tc_stats = nullptr;   // device [8]; set by dcu_deb
 // consumer runs the phase-collapsed 2x2 kernels on it (`in` is then the hin/2 x win/2 tensor).
 static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, float* out, int n, int hin, int win,
                    const HeadFuse* hf, cudaStream_t s, bool fuse_up = false, const FlatIn* fin = nullptr,
-                   const H2Layout* lout = nullptr) {
+                   const H2Layout* lout = nullptr, const FirstIn* first = nullptr) {
   const bool up_in = fuse_up && l.ups_in;
-  if ((fin || lout) && !(impl == DCU_CONV_TCGEN05 && e->tc_pair)) return fail(DCU_ERR_INVALID, "flat layouts need the CTA-pair kernel");
+  if ((fin || lout || first) && !(impl == DCU_CONV_TCGEN05 && e->tc_pair)) return fail(DCU_ERR_INVALID, "flat layouts / conv1a fusion need the CTA-pair kernel");
   ConvParams p{};
   p.in = in; p.out = out; p.bias = l.bias.as<float>(); p.alpha = l.alpha.as<float>(); p.beta = l.beta.as<float>();
   p.n = n; p.cin = l.cin; p.cout_total = l.cout; p.hin = up_in ? hin / 2 : hin; p.win = up_in ? win / 2 : win;
@@ -519,8 +533,9 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
   p.host_bn = &l.host_bn;
   if (fin) { p.flat_in = 1; p.in_period = fin->period; p.in_row = fin->row; }
   if (lout) p.out_layout = *lout;
+  if (first) { p.first_u8 = first->u8; p.first_f32 = first->f32; p.first_w = first->w; p.in = e->act[0].as<float>(); in = p.in; }
   if (n <= 0) return DCU_OK;
-  e->prof_begin(0, 2.0 * 9.0 * l.cin * l.cout * (double)p.hout * p.wout * n, s, l.cin, l.cout, p.hout, p.wout, n);
+  e->prof_begin(0, 2.0 * 9.0 * (l.cin + (first ? 1 : 0)) * l.cout * (double)p.hout * p.wout * n, s, l.cin, l.cout, p.hout, p.wout, n);
   double issued = 0.0;
   if (impl == DCU_CONV_TCGEN05) {
     if (l.tc_nt == 0) return fail(DCU_ERR_UNSUPPORTED, "layer shape not supported by the tcgen05 kernel");
@@ -576,7 +591,10 @@ static int detector_group(DcuEngine* e, const uint8_t* frames, const float* imag
   // stream while the tensor-core kernels of micro-batch i run on the caller's stream (double-buffered conv1a output).
   const bool h2 = e->conv_impl == DCU_CONV_TCGEN05;
   const int n_mb = (n + e->mb1 - 1) / e->mb1;
-  const bool overlap = e->overlap_first && n_mb > 1 && !e->profiling;
+  // conv1a computed inside conv1b's kernel (pair kernel only): no conv1a launch, no 19.7 MB / frame round trip through HBM
+  const bool fused_first = e->fuse_first && h2 && e->tc_pair && e->det[0].tc_nt == 64 && e->det_first.out_bound < 60000.f &&
+                           (frames != nullptr || e->f32_in_range);
+  const bool overlap = e->overlap_first && n_mb > 1 && !e->profiling && !fused_first;
   auto first = [&](int i, cudaStream_t st) -> int {
     const int f0 = i * e->mb1, m = std::min(e->mb1, n - f0);
     return run_first(e, e->det_first, frames ? frames + (size_t)f0 * H * W : nullptr,
@@ -598,9 +616,13 @@ static int detector_group(DcuEngine* e, const uint8_t* frames, const float* imag
         CK(cudaEventRecord(e->ev_done[(i + 1) & 1], e->side));
       }
       CK(cudaStreamWaitEvent(s, e->ev_done[i & 1], 0));
-    } else {
+    } else if (!fused_first) {
       if ((rc = first(i, s))) return rc;                                                                         // conv1a
     }
+    if (fused_first) {
+      const FirstIn fi{frames ? frames + (size_t)f0 * H * W : nullptr, images ? images + (size_t)f0 * H * W : nullptr, &e->det_first.host};
+      if ((rc = run_3x3(e, e->det[0], e->conv_impl, nullptr, a1, m, H, W, nullptr, s, false, nullptr, nullptr, &fi))) return rc;   // conv1a + conv1b + pool
+    } else
     if ((rc = run_3x3(e, e->det[0], e->conv_impl, c1, a1, m, H, W, nullptr, s))) return rc;                     // conv1b + pool
     if (overlap) CK(cudaEventRecord(e->ev_free[i & 1], s));
     if ((rc = run_3x3(e, e->det[1], e->conv_impl, a1, a0, m, H / 2, W / 2, nullptr, s))) return rc;             // conv2a
@@ -834,6 +856,7 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   if (const char* v = getenv("DCU_OVERLAP_FIRST")) e->overlap_first = atoi(v) != 0;
   if (const char* v = getenv("DCU_TC_PAIR")) e->tc_pair = atoi(v) != 0;
   if (const char* v = getenv("DCU_FUSE_UP")) e->fuse_up = atoi(v) != 0;
+  if (const char* v = getenv("DCU_FUSE_FIRST")) e->fuse_first = atoi(v) != 0;
   if (const char* v = getenv("DCU_GRAPH")) e->use_graphs = atoi(v) != 0;
   if (const char* v = getenv("DCU_GRAPH_MAX_N")) e->graph_max_n = std::max(0, atoi(v));
   TRYC(cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking));

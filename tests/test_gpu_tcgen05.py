@@ -95,3 +95,32 @@ def test_tcgen05_deterministic_and_batch_invariant(tc_models):
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
     one = dc.infer_batch(frames[5:6], 16, deepc, refinenet)[0]
     assert np.array_equal(one, a[5])
+
+
+def test_fused_first_layer_is_bit_identical(states, golden_synth, monkeypatch):
+    """conv1a computed inside conv1b's kernel (conv_tc2.cu FIRST mode, the default) vs the separate conv1a kernel + HBM round trip
+    (DCU_FUSE_FIRST=0): same FMA order for conv1a, same MMAs for conv1b -> bit-identical logits, for u8 and fp32 inputs, at a
+    size with ragged tiles too."""
+    import torch
+    for (H, W) in ((240, 320), (200, 296)):
+        frames = np.ascontiguousarray(golden_synth["frames"][:5, :H, :W])
+        outs = {}
+        for fuse in ("1", "0"):
+            monkeypatch.setenv("DCU_FUSE_FIRST", fuse)
+            e = N.Engine(states[0], states[1], H, W, 16, 0, max_batch=8, max_patches=1024)
+            try:
+                fr = torch.from_numpy(frames).cuda()
+                x = torch.from_numpy(np.stack([oracle.pre_bgr_image(f)[0] for f in frames])).cuda()
+                res = []
+                for entry, src in ((N.lib().dcu_detector_forward, fr), (N.lib().dcu_detector_forward_f32, x)):
+                    loc = torch.empty((5, 65, H // 8, W // 8), device="cuda")
+                    ids = torch.empty((5, 17, H // 8, W // 8), device="cuda")
+                    N.check(entry(e.handle, src.data_ptr(), 5, loc.data_ptr(), ids.data_ptr(), None))
+                    torch.cuda.synchronize()
+                    res += [loc.cpu().numpy(), ids.cpu().numpy()]
+                outs[fuse] = res
+            finally:
+                e.close()
+        for a, b in zip(outs["1"], outs["0"]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(outs["1"][0], outs["1"][2])          # u8 entry == fp32 entry
