@@ -301,7 +301,9 @@ struct DcuEngine {
   cudaEvent_t ev_start = nullptr, ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   bool overlap_first = true;
   bool f32_in_range = true;     // fp32 image inputs are normalised ((x-128)/255, |x| <= 0.51): required by the fused kernel's bound
-  bool fuse_first = true;       // detector: conv1a inside conv1b's kernel (DCU_FUSE_FIRST=0: separate conv1a kernel + HBM round trip)
+  bool fuse_first = false;      // detector: conv1a inside conv1b's kernel (DCU_FUSE_FIRST=1).  Off by default: bit-identical and 39 MB / frame less
+                                // DRAM traffic, but the CUDA-core producers pace the kernel (tensor pipe 57 % instead of 84 % active) and the step
+                                // time is the same within 1 %
   bool fuse_up = true;          // RefineNet: fold the 2x nearest upsamplings into the consuming convolution (DCU_FUSE_UP=0: materialise)
   bool flat = true;             // RefineNet maps up to conv4a's input as F2 runs (conv_tc2.cu FLAT mode; DCU_FLAT=0: per-patch tiles)
   DevBuf flat8[3];              // 8x8 maps in 9x9 cells (conv2b / conv3a / conv3b outputs); gutters stay zero
