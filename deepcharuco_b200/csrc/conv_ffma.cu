@@ -10,6 +10,8 @@
 // cross-check for the tcgen05 path in conv_tc.cu.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dcu {
@@ -321,9 +323,95 @@ conv_first_kernel(FirstConvParams p, long long total_px) {
   }
 }
 
+// Row-streaming variant for wide maps (the detector's conv1a: 76.8k pixels and 19.7 MB of output per frame).  The kernel above
+// re-reads its 576 weights from shared memory for every pixel (144 LDS.128) and is bound by the L1 / shared data pipe (ncu: 82 %)
+// at 42 % of the HBM write rate.  Here a warp owns ONE group of 8 output channels and keeps its 72 weights + 24 BN constants in
+// registers (plain register FFMA operands; constant-bank operands were tried and are slow: indexed LDC issues ~1 per 15 cycles per
+// SM), lanes are 32 adjacent pixels, and the warp walks down FR_ROWS rows with a rolling 3x3 window fed from a small shared tile
+// of the NORMALISED input (3 LDS per pixel instead of 144).  A block = 8 warps = all 64 channels of a 32-pixel-wide strip, so
+// every store instruction writes 512 contiguous bytes of one H2 plane.  FMA order per output (taps 0..8 ascending, from 0) is the
+// same as above: bit-identical results.
+constexpr int FR_ROWS = 30;
+template <bool kU8>
+__global__ void __launch_bounds__(256, 2)
+conv_first_rows_kernel(const FirstConvParams p, int strips_x, int row_blocks) {
+  __shared__ float tile[(FR_ROWS + 2) * 34];
+  const int lane = threadIdx.x & 31, g8 = threadIdx.x >> 5;
+  int item = blockIdx.x;
+  const int sx = item % strips_x; item /= strips_x;
+  const int rb = item % row_blocks;
+  const int img = item / row_blocks;
+  const int x0 = sx * 32, y0 = rb * FR_ROWS;
+  const int rows = min(FR_ROWS, p.hout - y0);
+  // normalised input tile [rows + 2][34] with the layer's zero padding (applied to the NORMALISED image, net.py:23)
+  {
+    const size_t in_base = (size_t)img * p.hin * p.win;
+    for (int i = threadIdx.x; i < (rows + 2) * 34; i += 256) {
+      const int ty = i / 34, tx = i - ty * 34;
+      const int gy = y0 - p.pad + ty, gx = x0 - p.pad + tx;
+      float v = 0.f;
+      if (gy >= 0 && gy < p.hin && gx >= 0 && gx < p.win) {
+        const size_t o = in_base + (size_t)gy * p.win + gx;
+        v = kU8 ? __fdiv_rn((float)p.in_u8[o] - 128.0f, 255.0f) : p.in_f32[o];      // (x - 128) / 255, model_utils.py:48-49
+      }
+      tile[i] = v;
+    }
+  }
+  float w[9][8], bi[8], al[8], be[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.w + t * 64 + g8 * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.w + t * 64 + g8 * 8 + 4));
+    w[t][0] = a.x; w[t][1] = a.y; w[t][2] = a.z; w[t][3] = a.w; w[t][4] = b.x; w[t][5] = b.y; w[t][6] = b.z; w[t][7] = b.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { bi[j] = __ldg(p.bias + g8 * 8 + j); al[j] = __ldg(p.alpha + g8 * 8 + j); be[j] = __ldg(p.beta + g8 * 8 + j); }
+  __syncthreads();
+  const int ox = x0 + lane;
+  const H2Layout lay = p.out_layout.plane ? p.out_layout : h2_standard(64, p.hout, p.wout);
+  uint4* outh = reinterpret_cast<uint4*>(p.out) + (size_t)img * lay.img + (size_t)g8 * lay.plane + (size_t)y0 * lay.row + ox;
+  float v[9];
+#pragma unroll
+  for (int t = 0; t < 6; ++t) v[t] = tile[(t / 3) * 34 + lane + (t % 3)];
+#pragma unroll 1
+  for (int r = 0; r < rows; ++r) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) v[6 + kx] = tile[(r + 2) * 34 + lane + kx];
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = fmaf(v[t], w[t][j], y[j]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = bn_relu(y[j], bi[j], al[j], be[j]);
+    if (ox < p.wout) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split_h2(y[2 * e], y[2 * e + 1], h[e], l[e]);
+      uint4* o = outh + (size_t)r * lay.row;
+      o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+      o[lay.lo] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+#pragma unroll
+    for (int t = 0; t < 6; ++t) v[t] = v[t + 3];
+  }
+}
+
 void launch_conv_first(const FirstConvParams& p, cudaStream_t s) {
   const long long total = (long long)p.n * p.hout * p.wout;
   if (total <= 0) return;
+  static const bool rows_ok = [] { const char* v = getenv("DCU_FIRST_ROWS"); return !v || atoi(v) != 0; }();
+  if (p.out_h2 && p.wout >= 64 && p.pad == 1 && rows_ok) {
+    const int strips_x = ceil_div(p.wout, 32), row_blocks = ceil_div(p.hout, FR_ROWS);
+    const long long items = (long long)p.n * strips_x * row_blocks;
+    if (items < 0x7fffffffLL) {
+      if (p.in_u8 != nullptr) conv_first_rows_kernel<true><<<(int)items, 256, 0, s>>>(p, strips_x, row_blocks);
+      else conv_first_rows_kernel<false><<<(int)items, 256, 0, s>>>(p, strips_x, row_blocks);
+      return;
+    }
+  }
   long long blocks = (total + 127) / 128;
   const long long cap = 148LL * 32;
   if (blocks > cap) blocks = cap;
