@@ -297,6 +297,13 @@ struct DcuEngine {
   DevBuf act[2];                // ping-pong activation buffers
   DevBuf c1[2];                 // conv1a outputs, double-buffered: conv1a of micro-batch i+1 (HBM-write bound, side stream)
                                 // overlaps conv1b/2a/2b of micro-batch i (tensor bound, caller's stream)
+  // host entry point: the frames are copied in micro-batch sized chunks on `copy`, and the first layer of micro-batch i waits for
+  // chunk i only, so all but the first chunk's transfer hides behind the previous micro-batch's kernels
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev_copy_start = nullptr;
+  std::vector<cudaEvent_t> h2d_ev;
+  bool h2d_active = false;
+  int h2d_base = 0;                     // chunk index of the current group's first micro-batch
   cudaStream_t side = nullptr;
   cudaEvent_t ev_start = nullptr, ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   bool overlap_first = true;
@@ -304,6 +311,7 @@ struct DcuEngine {
   bool fuse_first = false;      // detector: conv1a inside conv1b's kernel (DCU_FUSE_FIRST=1).  Off by default: bit-identical and 39 MB / frame less
                                 // DRAM traffic, but the CUDA-core producers pace the kernel (tensor pipe 57 % instead of 84 % active) and the step
                                 // time is the same within 1 %
+  bool chunked_h2d = true;      // DCU_CHUNKED_H2D=0: one copy of the whole batch on the caller's stream before the first kernel
   bool fuse_up = true;          // RefineNet: fold the 2x nearest upsamplings into the consuming convolution (DCU_FUSE_UP=0: materialise)
   bool flat = true;             // RefineNet maps up to conv4a's input as F2 runs (conv_tc2.cu FLAT mode; DCU_FLAT=0: per-patch tiles)
   DevBuf flat8[3];              // 8x8 maps in 9x9 cells (conv2b / conv3a / conv3b outputs); gutters stay zero
@@ -352,6 +360,9 @@ struct DcuEngine {
 
   ~DcuEngine() {
     if (side) cudaStreamDestroy(side);
+    if (copy) cudaStreamDestroy(copy);
+    if (ev_copy_start) cudaEventDestroy(ev_copy_start);
+    for (auto ev : h2d_ev) cudaEventDestroy(ev);
     for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (gstream) cudaStreamDestroy(gstream);
     if (ev_start) cudaEventDestroy(ev_start);
@@ -599,6 +610,8 @@ static int detector_group(DcuEngine* e, const uint8_t* frames, const float* imag
   const bool overlap = e->overlap_first && n_mb > 1 && !e->profiling && !fused_first;
   auto first = [&](int i, cudaStream_t st) -> int {
     const int f0 = i * e->mb1, m = std::min(e->mb1, n - f0);
+    if (e->h2d_active && cudaStreamWaitEvent(st, e->h2d_ev[e->h2d_base + i], 0) != cudaSuccess)
+      return fail(DCU_ERR_CUDA, "cudaStreamWaitEvent (chunked H2D) failed");
     return run_first(e, e->det_first, frames ? frames + (size_t)f0 * H * W : nullptr,
                      images ? images + (size_t)f0 * H * W : nullptr, e->c1[i & 1].as<float>(), m, H, W, h2, st);
   };
@@ -622,6 +635,7 @@ static int detector_group(DcuEngine* e, const uint8_t* frames, const float* imag
       if ((rc = first(i, s))) return rc;                                                                         // conv1a
     }
     if (fused_first) {
+      if (e->h2d_active) CK(cudaStreamWaitEvent(s, e->h2d_ev[e->h2d_base + i], 0));
       const FirstIn fi{frames ? frames + (size_t)f0 * H * W : nullptr, images ? images + (size_t)f0 * H * W : nullptr, &e->det_first.host};
       if ((rc = run_3x3(e, e->det[0], e->conv_impl, nullptr, a1, m, H, W, nullptr, s, false, nullptr, nullptr, &fi))) return rc;   // conv1a + conv1b + pool
     } else
@@ -858,6 +872,9 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   if (const char* v = getenv("DCU_OVERLAP_FIRST")) e->overlap_first = atoi(v) != 0;
   if (const char* v = getenv("DCU_TC_PAIR")) e->tc_pair = atoi(v) != 0;
   if (const char* v = getenv("DCU_FUSE_UP")) e->fuse_up = atoi(v) != 0;
+  if (const char* v = getenv("DCU_CHUNKED_H2D")) e->chunked_h2d = atoi(v) != 0;
+  TRYC(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
+  TRYC(cudaEventCreateWithFlags(&e->ev_copy_start, cudaEventDisableTiming));
   if (const char* v = getenv("DCU_FUSE_FIRST")) e->fuse_first = atoi(v) != 0;
   if (const char* v = getenv("DCU_GRAPH")) e->use_graphs = atoi(v) != 0;
   if (const char* v = getenv("DCU_GRAPH_MAX_N")) e->graph_max_n = std::max(0, atoi(v));
@@ -1071,6 +1088,7 @@ int dcu_infer_batch(DcuEngine* e, const uint8_t* frames_dev, int n, int dust_bin
   for (int f0 = 0; f0 < n; f0 += e->mb2) {
     const int m = std::min(e->mb2, n - f0);
     const uint8_t* fr = frames_dev + (size_t)f0 * H * W;
+    e->h2d_base = f0 / e->mb1;
     if ((rc = detector_group(e, fr, nullptr, m, e->loc.as<float>(), e->ids.as<float>(), s))) return rc;
     if ((rc = decode_group(e, e->loc.as<float>(), e->ids.as<float>(), fr, m, dust_bin_ids, f0 > 0, counts_dev + f0,
                            offsets_dev + f0, total_dev, kpts_dev, use_refinenet ? e->patches.as<float>() : nullptr, s)))
@@ -1229,12 +1247,30 @@ static int infer_batch_host_impl(DcuEngine* e, const uint8_t* frames_host, int n
     launch_bgr_to_gray(e->bgr.as<uint8_t>(), e->frames.as<uint8_t>(), (long long)gbytes, s);
     e->launches++;
     CK(cudaGetLastError());
+  } else if (e->chunked_h2d && n > e->mb1 && (e->mb2 % e->mb1) == 0 && !e->profiling) {
+    const size_t frame_bytes = (size_t)e->cfg.height * e->cfg.width;
+    const int n_chunks = (n + e->mb1 - 1) / e->mb1;
+    while ((int)e->h2d_ev.size() < n_chunks) {
+      cudaEvent_t ev;
+      CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      e->h2d_ev.push_back(ev);
+    }
+    CK(cudaEventRecord(e->ev_copy_start, s));                  // earlier work on the caller's stream may still read e->frames
+    CK(cudaStreamWaitEvent(e->copy, e->ev_copy_start, 0));
+    for (int c = 0; c < n_chunks; ++c) {
+      const int f0 = c * e->mb1, m = std::min(e->mb1, n - f0);
+      CK(cudaMemcpyAsync(e->frames.as<uint8_t>() + (size_t)f0 * frame_bytes, src + (size_t)f0 * frame_bytes, (size_t)m * frame_bytes,
+                         cudaMemcpyHostToDevice, e->copy));
+      CK(cudaEventRecord(e->h2d_ev[c], e->copy));
+    }
+    e->h2d_active = true;
   } else {
     CK(cudaMemcpyAsync(e->frames.p, src, fbytes, cudaMemcpyHostToDevice, s));
   }
   int rc = dcu_infer_batch(e, e->frames.as<uint8_t>(), n, dust_bin_ids, use_refinenet, e->counts.as<int32_t>(),
                            e->offsets.as<int32_t>(), e->total.as<int32_t>(), e->kpts.as<int32_t>(),
                            e->refined.as<float>(), s);
+  e->h2d_active = false;
   if (rc) return rc;
   int total;
   if (use_refinenet) {
