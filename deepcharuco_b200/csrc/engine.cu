@@ -57,6 +57,11 @@ struct Layer3x3 {
   CUtensorMap wmap_up[2];
   float up_scale = 1.f;
   int tc_nt = 0;              // N per CTA pass for the tcgen05 kernel (64 / 128), 0 = unsupported
+  // the same layer in 64-channel slices (layers whose tc_nt is 128): used for launches with fewer work items than SMs (small
+  // batches / single frames), where twice as many, half as long CTA-pair tiles cut the latency of the launch
+  DevBuf w_tc2_64[2], w_up_64[2];
+  CUtensorMap wmap2_64[2], wmap_up_64[2];
+  bool has_64 = false;
   DevBuf bias, alpha, beta;   // [cout]
   TcBn host_bn{};             // the same three vectors, passed by value to the pair kernel
 };
@@ -311,6 +316,7 @@ struct DcuEngine {
   bool fuse_first = false;      // detector: conv1a inside conv1b's kernel (DCU_FUSE_FIRST=1).  Off by default: bit-identical and 39 MB / frame less
                                 // DRAM traffic, but the CUDA-core producers pace the kernel (tensor pipe 57 % instead of 84 % active) and the step
                                 // time is the same within 1 %
+  bool small_slices = true;     // DCU_SMALL_SLICES=0: never switch 128-channel layers to 64-channel slices for small launches
   bool chunked_h2d = true;      // DCU_CHUNKED_H2D=0: one copy of the whole batch on the caller's stream before the first kernel
   bool fuse_up = true;          // RefineNet: fold the 2x nearest upsamplings into the consuming convolution (DCU_FUSE_UP=0: materialise)
   bool flat = true;             // RefineNet maps up to conv4a's input as F2 runs (conv_tc2.cu FLAT mode; DCU_FLAT=0: per-patch tiles)
@@ -372,8 +378,8 @@ struct DcuEngine {
     for (DevBuf* b : all) b->release();
     FirstLayer* fl[] = {&det_first, &ref_first};
     for (FirstLayer* f : fl) { f->w.release(); f->bias.release(); f->alpha.release(); f->beta.release(); }
-    for (Layer3x3& l : det) { l.w_tc2[0].release(); l.w_tc2[1].release(); l.w_ffma.release(); l.w_tc.release(); l.bias.release(); l.alpha.release(); l.beta.release(); }
-    for (Layer3x3& l : ref) { l.w_up[0].release(); l.w_up[1].release(); l.w_tc2[0].release(); l.w_tc2[1].release(); l.w_ffma.release(); l.w_tc.release(); l.bias.release(); l.alpha.release(); l.beta.release(); }
+    for (Layer3x3& l : det) { l.w_tc2_64[0].release(); l.w_tc2_64[1].release(); l.w_up_64[0].release(); l.w_up_64[1].release(); l.w_tc2[0].release(); l.w_tc2[1].release(); l.w_ffma.release(); l.w_tc.release(); l.bias.release(); l.alpha.release(); l.beta.release(); }
+    for (Layer3x3& l : ref) { l.w_tc2_64[0].release(); l.w_tc2_64[1].release(); l.w_up_64[0].release(); l.w_up_64[1].release(); l.w_up[0].release(); l.w_up[1].release(); l.w_tc2[0].release(); l.w_tc2[1].release(); l.w_ffma.release(); l.w_tc.release(); l.bias.release(); l.alpha.release(); l.beta.release(); }
     for (auto& r : prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto ev : ev_pool) cudaEventDestroy(ev);
     if (h_frames) cudaFreeHost(h_frames);
@@ -477,6 +483,24 @@ int build_3x3(Layer3x3& l, std::vector<const DcuConvLayer*> parts, int pad, int 
       }
       l.ups_in = true;
     }
+    if (l.tc_nt == 128) {
+      for (int r = 0; r < 2; ++r) {
+        const std::vector<uint16_t> pb = pack_tc_pair(ws, couts, cin, 64, l.tc_scale, r);
+        CK(l.w_tc2_64[r].alloc(pb.size() * 2));
+        CK(cudaMemcpy(l.w_tc2_64[r].p, pb.data(), pb.size() * 2, cudaMemcpyHostToDevice));
+        if ((rc = encode_weight_map(&l.wmap2_64[r], l.w_tc2_64[r].p, pb.size() * 2, 64, 0))) return rc;
+      }
+      if (l.ups_in) {
+        const std::vector<double> comb = collapse_up_weights(ws[0], l.cout, cin);
+        for (int r = 0; r < 2; ++r) {
+          const std::vector<uint16_t> pb = pack_tc_pair_up(comb, l.cout, cin, 64, l.up_scale, r);
+          CK(l.w_up_64[r].alloc(pb.size() * 2));
+          CK(cudaMemcpy(l.w_up_64[r].p, pb.data(), pb.size() * 2, cudaMemcpyHostToDevice));
+          if ((rc = encode_weight_map(&l.wmap_up_64[r], l.w_up_64[r].p, pb.size() * 2, 64, 1))) return rc;
+        }
+      }
+      l.has_64 = true;
+    }
   }
   return DCU_OK;
 }
@@ -560,9 +584,19 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
                      : make_tmap(&tm, in, n, l.cin, hin, win, 8 * g.tc + 2, 16 * g.tr + 2);
     if (rc) return rc;
     if (fuse_up && !e->tc_pair) return fail(DCU_ERR_INVALID, "upsample fusion needs the CTA-pair kernel");
+    // few work items (small batch): 64-channel slices -> twice the items, half the MMA chain per item
+    bool use64 = false;
+    if (e->tc_pair && l.has_64 && e->small_slices) {
+      const long long px = fin ? (long long)n * fin->period : (long long)n * (up_in ? p.hin * p.win * 2 : p.hout * p.wout);
+      const long long items128 = ((px + 511) / 512) * (l.cout / 128) * (up_in ? 2 : 1);
+      use64 = items128 < e->sm_count / 2;
+    }
+    const int nt_use = use64 ? 64 : l.tc_nt;
     cudaError_t ce = e->tc_pair
-                         ? (up_in ? launch_conv_tc2(p, l.cout / l.tc_nt, 1, &tm, &l.wmap_up[0], &l.wmap_up[1], e->sm_count, s, &issued)
-                                  : launch_conv_tc2(p, l.cout / l.tc_nt, 0, &tm, &l.wmap2[0], &l.wmap2[1], e->sm_count, s, &issued))
+                         ? (up_in ? launch_conv_tc2(p, l.cout / nt_use, 1, &tm, use64 ? &l.wmap_up_64[0] : &l.wmap_up[0],
+                                                    use64 ? &l.wmap_up_64[1] : &l.wmap_up[1], e->sm_count, s, &issued)
+                                  : launch_conv_tc2(p, l.cout / nt_use, 0, &tm, use64 ? &l.wmap2_64[0] : &l.wmap2[0],
+                                                    use64 ? &l.wmap2_64[1] : &l.wmap2[1], e->sm_count, s, &issued))
                          : launch_conv3x3_tc(p, l.w_tc.as<float>(), l.cout / l.tc_nt, l.tc_copies, &tm, e->sm_count, s);
     if (ce != cudaSuccess) return fail(DCU_ERR_CUDA, std::string("tcgen05 conv launch: ") + cudaGetErrorString(ce));
   } else {
@@ -873,6 +907,7 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   if (const char* v = getenv("DCU_TC_PAIR")) e->tc_pair = atoi(v) != 0;
   if (const char* v = getenv("DCU_FUSE_UP")) e->fuse_up = atoi(v) != 0;
   if (const char* v = getenv("DCU_CHUNKED_H2D")) e->chunked_h2d = atoi(v) != 0;
+  if (const char* v = getenv("DCU_SMALL_SLICES")) e->small_slices = atoi(v) != 0;
   TRYC(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
   TRYC(cudaEventCreateWithFlags(&e->ev_copy_start, cudaEventDisableTiming));
   if (const char* v = getenv("DCU_FUSE_FIRST")) e->fuse_first = atoi(v) != 0;
