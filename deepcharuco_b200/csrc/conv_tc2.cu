@@ -311,6 +311,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NBUF * MT);
   float* in_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES);     // FIRST: input window of the tile
 
+  // Programmatic dependent launch (launch attribute set by launch_pair): let the NEXT kernel of the stream start its prologue
+  // (barrier init, TMEM allocation, tensor-map and weight prefetch) on SMs this grid leaves idle or has left; it blocks in its own
+  // griddepcontrol.wait until this grid has completed and flushed.  Without the attribute both instructions are no-ops.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -383,6 +387,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           pre[k] = v;
         }
       };
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       prefetch(cluster_id);
       int st = 0; uint32_t ph = 0, wb = 0;
       for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
@@ -461,6 +466,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   } else if (!FIRST && warp == 0 && lane == 0) {
     // ================= activation producer: this CTA's halo into this CTA's smem, bytes credited to the leader =================
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");        // the activations are the previous kernel's output (weights are not: no wait there)
     int st = 0; uint32_t ph = 0;
     for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
       const Tile2 c = decode_pair_tile(pt, rank, g);
@@ -568,6 +574,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int c8_out = p.cout_total >> 3;
     uint32_t phc = 0;
     int buf = 0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");        // (ordered anyway through the activation loads; keeps the stores formally after the wait)
     for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
       const Tile2 c = decode_pair_tile(pt, rank, g);
       mbar_wait<200>(&acc_full[buf], phc);
@@ -749,13 +756,21 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
   if (issued_flops) *issued_flops = 2.0 * (double)g.total_pairs * (p.cin / 16) * (UP ? 4 : KS * KS) * Cfg::MT * 256.0 * 3.0 * NT * 16.0;
   const long long clusters = g.total_pairs < sm_count / 2 ? g.total_pairs : sm_count / 2;
   if (p.host_bn == nullptr) return cudaErrorInvalidValue;
+  static const bool pdl = [] { const char* v = getenv("DCU_PDL"); return !v || atoi(v) != 0; }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)clusters * 2, 1, 1); cfg.blockDim = dim3(T2_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
   if constexpr (FIRST) {
     if (p.first_w == nullptr || (!p.first_u8 && !p.first_f32) || p.cin != 64 || p.pad != 1 || g.flat ||
         (g.halo_w + 2) * (g.halo_h + 2) > Cfg::WIN_ELEMS || (g.halo_w + 2) * (g.halo_h + 2) > 576 || g.halo_w * g.halo_h > 384)
       return cudaErrorInvalidValue;
-    conv_tc2_kernel<NT, KS, UP, WRES, true><<<(int)clusters * 2, T2_THREADS, Cfg::SMEM_BYTES, s>>>(*ta, *w0, *w1, p, g, *p.host_bn, *p.first_w);
+    return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, KS, UP, WRES, true>, *ta, *w0, *w1, p, g, *p.host_bn, *p.first_w);
   } else {
-    conv_tc2_kernel<NT, KS, UP, WRES, false><<<(int)clusters * 2, T2_THREADS, Cfg::SMEM_BYTES, s>>>(*ta, *w0, *w1, p, g, *p.host_bn, NoFirst());
+    return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, KS, UP, WRES, false>, *ta, *w0, *w1, p, g, *p.host_bn, NoFirst());
   }
   return cudaGetLastError();
 }
