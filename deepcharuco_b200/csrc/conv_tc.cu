@@ -253,6 +253,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
   uint64_t* acc_empty = acc_full + NBUF;           // [NBUF][MT] m-tile drained by the epilogue (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NBUF * MT);
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");         // programmatic dependent launch, see conv_tc2.cu
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (keeps role code on the uniform datapath)
   const int lane = threadIdx.x & 31;
   const int chunks = p.cin >> 4;
@@ -282,6 +283,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
   if (warp == 0 && lane == 0) {
     // ================= activation producer (TMA) =================
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");        // activations = the previous kernel's output
     int st = 0; uint32_t ph = 0;
     for (long long t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       const TileCoord c = decode_tile(t, g);
@@ -559,8 +561,15 @@ static cudaError_t launch_nt(const ConvParams& p, const float* w_blocks, int n_s
   g.total_tiles = (long long)p.n * g.slices * g.tiles_x * g.tiles_y;
   if (g.total_tiles <= 0) return cudaSuccess;
   const int grid = (int)(g.total_tiles < sm_count ? g.total_tiles : sm_count);
-  conv3x3_tc_kernel<NT, KS><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(*tm, p, w_blocks, g);
-  return cudaGetLastError();
+  static const bool pdl = [] { const char* v = getenv("DCU_PDL"); return !v || atoi(v) != 0; }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1); cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NT, KS>, *tm, p, w_blocks, g);
 }
 
 cudaError_t launch_conv3x3_tc(const ConvParams& p, const float* w_blocks, int n_slices, int w_copies, const void* tmap_in,
