@@ -68,6 +68,7 @@ struct ConvParams {
   // are the data extents inside it); conv_tc2.cu FLAT mode.
   H2Layout out_layout;
   int flat_in, in_period, in_row;
+  int mt1;                      // pair kernel: one m-tile (16 x 8 pixels) per CTA -- small launches; the caller's tensor map box is 10 x 18 pixels
   const struct TcBn* host_bn;   // host copy of bias / alpha / beta: the pair kernel takes them by value (constant bank)
   // FIRST mode of the pair kernel: `in` is unused; the 64 input channels are conv1a (+BN+ReLU) of the frames, computed in-kernel
   const struct FirstWeights* first_w;   // host copy of conv1a's weights / BN constants, or null

@@ -54,9 +54,11 @@ constexpr int T2_THREADS = 384;
 // WRES (weights resident): a 64 -> 64 layer's whole weight set (4 chunks x 3 kernel rows = 12 stages, 110.6 kB per rank) stays in
 // shared memory for the lifetime of the CTA instead of being re-fetched for every tile.  The kernel is bound by the shared-memory
 // data pipe (tensor-core operand fetches + fills, profiles/r1_ncu_conv_tc2.txt: 77 % + 23 %); the weight refills were 10 % of it.
-template <int NT, bool UP = false, bool WRES = false>
+// MT_ = 1: one 128-pixel m-tile per CTA (16 x 8 pixels) instead of two -- launches with few work items (single frames) get twice
+// the items with half the MMA chain each; not for UP (its two m-tiles are the column phases) or FLAT.
+template <int NT, bool UP = false, bool WRES = false, int MT_ = 2>
 struct Tc2Cfg {
-  static constexpr int MT = 2;
+  static constexpr int MT = MT_;
   static constexpr int STAGE_BLOCKS = UP ? 4 : 3;                  // weight blocks per stage (one kernel row; UP: 2 taps x 2 column phases)
   static constexpr int NBUF = 512 / (MT * 2 * NT);
   static constexpr int A_STAGES = 4;
@@ -285,14 +287,14 @@ __device__ __forceinline__ Tile2 decode_pair_tile(long long pt, uint32_t rank, c
 }
 
 struct NoFirst {};
-template <int NT, int KS, bool UP, bool WRES, bool FIRST>
+template <int NT, int KS, bool UP, bool WRES, bool FIRST, int MT_ = 2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w0,
                 const __grid_constant__ CUtensorMap tmap_w1, const ConvParams p, const Tc2Geo g, const __grid_constant__ TcBn bn,
                 const __grid_constant__ typename std::conditional<FIRST, FirstWeights, NoFirst>::type fw) {
   // bn: bias / BN scale / BN shift by value = constant bank.  The epilogue's channel index is warp-uniform, so these become
   // uniform constant loads instead of shared-memory reads (the shared-memory data pipe is what bounds this kernel).
-  using Cfg = Tc2Cfg<NT, UP, WRES>;
+  using Cfg = Tc2Cfg<NT, UP, WRES, MT_>;
   constexpr int MT = Cfg::MT, NBUF = Cfg::NBUF, B_STAGES = Cfg::B_STAGES;
   // UP (input = 2x nearest upsampling of the tensor in HBM): per output phase (a, b) the 3x3 taps collapse to 2x2 taps on
   // the low-resolution tensor, so a weight stage is one of 2 kernel rows = 2 taps x 2 column phases (see header).
@@ -703,20 +705,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
-template <int NT, int KS, bool UP, bool WRES = false, bool FIRST = false>
+template <int NT, int KS, bool UP, bool WRES = false, bool FIRST = false, int MT_ = 2>
 cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta, const CUtensorMap* w0, const CUtensorMap* w1,
                         int sm_count, cudaStream_t s, double* issued_flops) {
-  using Cfg = Tc2Cfg<NT, UP, WRES>;
+  using Cfg = Tc2Cfg<NT, UP, WRES, MT_>;
   static bool attr_done[64] = {};      // function attributes are per device: engines on several GPUs of one process each opt in
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NT, KS, UP, WRES, FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NT, KS, UP, WRES, FIRST, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   Tc2Geo g{};
   if (UP && (p.pad != 1 || p.pool || p.ups || p.hout != 2 * p.hin || p.wout != 2 * p.win)) return cudaErrorInvalidValue;
+  if (MT_ == 1 && (UP || p.flat_in)) return cudaErrorInvalidValue;
   if (p.flat_in) {
     // the batch as one run of pixels; CTA tile = 256 consecutive pixels (UP: 128, the two m-tiles are the column phases)
     if (p.pool || p.ups || p.head_w || p.logits || p.in_period <= 0 || p.in_row <= 0) return cudaErrorInvalidValue;
@@ -737,7 +740,7 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
     g.tiles_x = ceil_div(p.win, 8); g.tiles_y = ceil_div(p.hin, 16);
     n_slices *= 2;
   } else {
-    tc_tile_arrangement(NT, p.hout, p.wout, &g.tr, &g.tc);
+    if (MT_ == 1) { g.tr = 1; g.tc = 1; } else tc_tile_arrangement(NT, p.hout, p.wout, &g.tr, &g.tc);
     g.halo_w = 8 * g.tc + 2; g.halo_h = 16 * g.tr + 2;
     g.tiles_x = ceil_div(p.wout, 8 * g.tc); g.tiles_y = ceil_div(p.hout, 16 * g.tr);
   }
@@ -770,7 +773,7 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
       return cudaErrorInvalidValue;
     return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, KS, UP, WRES, true>, *ta, *w0, *w1, p, g, *p.host_bn, *p.first_w);
   } else {
-    return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, KS, UP, WRES, false>, *ta, *w0, *w1, p, g, *p.host_bn, NoFirst());
+    return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, KS, UP, WRES, false, MT_>, *ta, *w0, *w1, p, g, *p.host_bn, NoFirst());
   }
   return cudaGetLastError();
 }
@@ -801,6 +804,10 @@ cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const voi
     if (nt != 64 || n_slices != 1) return cudaErrorInvalidValue;
     return wres_ok ? launch_pair<64, 3, false, true, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops)
                    : launch_pair<64, 3, false, false, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+  }
+  if (p.mt1) {
+    if (nt != 64 || up) return cudaErrorInvalidValue;
+    return launch_pair<64, 3, false, false, false, 1>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
   }
   if (nt == 64 && n_slices == 1 && p.cin == 64 && wres_ok) return launch_pair<64, 3, false, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
   if (nt == 64) return launch_pair<64, 3, false>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);

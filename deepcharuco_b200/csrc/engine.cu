@@ -576,7 +576,16 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
   double issued = 0.0;
   if (impl == DCU_CONV_TCGEN05) {
     if (l.tc_nt == 0) return fail(DCU_ERR_UNSUPPORTED, "layer shape not supported by the tcgen05 kernel");
-    const TcGeom g = tc_geom(l.tc_nt, p.hout, p.wout);
+    TcGeom g = tc_geom(l.tc_nt, p.hout, p.wout);
+    // few work items (small batch): 64-channel slices -> twice the items, half the MMA chain per item; still few: one m-tile per CTA
+    bool use64 = false;
+    if (e->tc_pair && e->small_slices && (l.has_64 || l.tc_nt == 64)) {
+      const long long px = fin ? (long long)n * fin->period : (long long)n * (up_in ? p.hin * p.win * 2 : p.hout * p.wout);
+      const long long items128 = ((px + 511) / 512) * ((l.cout + 127) / 128) * (up_in ? 2 : 1);
+      use64 = l.has_64 && items128 < e->sm_count / 2;
+      const long long items64 = ((px + 511) / 512) * (l.cout / 64) * (up_in ? 2 : 1);
+      if ((use64 || l.tc_nt == 64) && !up_in && !fin && !first && items64 < e->sm_count / 2) { p.mt1 = 1; g.tr = 1; g.tc = 1; }
+    }
     CUtensorMap tm;
     int rc = fin ? make_tmap_flat(&tm, in, (long long)n * fin->period, l.cin, fin->plane_px,
                                   tc2_flat_rows(fin->row, (up_in || l.pad) ? 1 : 0, up_in ? 1 : 0))
@@ -584,13 +593,6 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
                      : make_tmap(&tm, in, n, l.cin, hin, win, 8 * g.tc + 2, 16 * g.tr + 2);
     if (rc) return rc;
     if (fuse_up && !e->tc_pair) return fail(DCU_ERR_INVALID, "upsample fusion needs the CTA-pair kernel");
-    // few work items (small batch): 64-channel slices -> twice the items, half the MMA chain per item
-    bool use64 = false;
-    if (e->tc_pair && l.has_64 && e->small_slices) {
-      const long long px = fin ? (long long)n * fin->period : (long long)n * (up_in ? p.hin * p.win * 2 : p.hout * p.wout);
-      const long long items128 = ((px + 511) / 512) * (l.cout / 128) * (up_in ? 2 : 1);
-      use64 = items128 < e->sm_count / 2;
-    }
     const int nt_use = use64 ? 64 : l.tc_nt;
     cudaError_t ce = e->tc_pair
                          ? (up_in ? launch_conv_tc2(p, l.cout / nt_use, 1, &tm, use64 ? &l.wmap_up_64[0] : &l.wmap_up[0],
