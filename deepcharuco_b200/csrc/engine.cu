@@ -334,7 +334,7 @@ struct DcuEngine {
   // Small batches (one frame per call is the reference's own benchmark loop, src/benchmark.py:38-53): ~27 launches of a few
   // microseconds each are launch-bound, so the whole fixed sequence  H2D -> detector -> decode -> RefineNet on a fixed number of
   // patch slots -> D2H  is captured once per (n, dust_bin, use_refinenet) and replayed as ONE cudaGraphLaunch.
-  struct SmallGraph { cudaGraphExec_t exec = nullptr; int n = 0, dust = 0, use_ref = 0, pfix = 0; int64_t launches = 0; bool dead = false; };
+  struct SmallGraph { cudaGraphExec_t exec = nullptr; int n = 0, dust = 0, use_ref = 0, pfix = 0, channels = 1; int64_t launches = 0; bool dead = false; };
   std::vector<SmallGraph> graphs;
   cudaStream_t gstream = nullptr;       // capture stream
   bool use_graphs = true;               // DCU_GRAPH=0: always launch kernel by kernel
@@ -939,7 +939,7 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   TRYC(cudaMemset(e->scan_state.p, 0, e->scan_state.bytes));
   TRYC(cudaMemset(e->total.p, 0, 16));
   TRYC(e->frames.alloc((size_t)cfg->max_batch * H * W));
-  TRYC(cudaMallocHost(&e->h_frames, (size_t)cfg->max_batch * H * W));
+  TRYC(cudaMallocHost(&e->h_frames, (size_t)cfg->max_batch * H * W * 3));      // grey or BGR frames
   TRYC(cudaMallocHost(&e->h_counts, (size_t)cfg->max_batch * 4));
   TRYC(cudaMallocHost(&e->h_offsets, (size_t)cfg->max_batch * 4));
   TRYC(cudaMallocHost(&e->h_kpts, (size_t)cfg->max_patches * 16));
@@ -1166,7 +1166,7 @@ int dcu_infer_batch_host_bgr(DcuEngine* e, const uint8_t* frames_host, int n, in
 }
 
 // Small-batch path: returns 1 if it did not handle the call (caller continues kernel by kernel), else a DCU_* status.
-static int infer_small_graph(DcuEngine* e, const uint8_t* frames_host, int n, int dust_bin_ids, int use_refinenet,
+static int infer_small_graph(DcuEngine* e, const uint8_t* frames_host, int n, int channels, int dust_bin_ids, int use_refinenet,
                              int32_t* counts_host, int32_t* offsets_host, int32_t* total_host, int32_t* kpts_host,
                              float* refined_host, cudaStream_t s) {
   const int H = e->cfg.height, W = e->cfg.width;
@@ -1177,10 +1177,10 @@ static int infer_small_graph(DcuEngine* e, const uint8_t* frames_host, int n, in
   const int pfix = std::min(per * n, e->cfg.max_patches);
   DcuEngine::SmallGraph* g = nullptr;
   for (auto& x : e->graphs)
-    if (x.n == n && x.dust == dust_bin_ids && x.use_ref == use_refinenet && x.pfix == pfix) g = &x;
+    if (x.n == n && x.dust == dust_bin_ids && x.use_ref == use_refinenet && x.pfix == pfix && x.channels == channels) g = &x;
   if (!g) {            // first call of this shape runs kernel by kernel (sets function attributes, allocates lazily)
     if (e->graphs.size() >= 64) return 1;
-    DcuEngine::SmallGraph x; x.n = n; x.dust = dust_bin_ids; x.use_ref = use_refinenet; x.pfix = pfix;
+    DcuEngine::SmallGraph x; x.n = n; x.dust = dust_bin_ids; x.use_ref = use_refinenet; x.pfix = pfix; x.channels = channels;
     e->graphs.push_back(x);
     return 1;
   }
@@ -1191,7 +1191,17 @@ static int infer_small_graph(DcuEngine* e, const uint8_t* frames_host, int n, in
     const int64_t l0 = e->launches;
     e->epoch_override = 0x3ffffff0u;
     int rc = DCU_OK;
-    cudaError_t ce = cudaMemcpyAsync(e->frames.p, e->h_frames, (size_t)n * H * W, cudaMemcpyHostToDevice, gs);
+    cudaError_t ce;
+    if (channels == 3) {            // BGR frames: cv2.cvtColor(BGR2GRAY) (inference.py:40) on the device, inside the graph
+      ce = cudaMemcpyAsync(e->bgr.p, e->h_frames, (size_t)n * H * W * 3, cudaMemcpyHostToDevice, gs);
+      if (ce == cudaSuccess) {
+        launch_bgr_to_gray(e->bgr.as<uint8_t>(), e->frames.as<uint8_t>(), (long long)n * H * W, gs);
+        e->launches++;
+        ce = cudaGetLastError();
+      }
+    } else {
+      ce = cudaMemcpyAsync(e->frames.p, e->h_frames, (size_t)n * H * W, cudaMemcpyHostToDevice, gs);
+    }
     if (ce == cudaSuccess) rc = detector_group(e, e->frames.as<uint8_t>(), nullptr, n, e->loc.as<float>(), e->ids.as<float>(), gs);
     if (ce == cudaSuccess && rc == DCU_OK) ce = cudaMemsetAsync(e->scan_state.p, 0, (size_t)n * 8, gs);
     if (ce == cudaSuccess && rc == DCU_OK)
@@ -1220,7 +1230,7 @@ static int infer_small_graph(DcuEngine* e, const uint8_t* frames_host, int n, in
     }
     cudaGraphDestroy(graph);
   }
-  std::memcpy(e->h_frames, frames_host, (size_t)n * H * W);
+  std::memcpy(e->h_frames, frames_host, (size_t)n * H * W * channels);
   CK(cudaGraphLaunch(g->exec, s));
   e->launches += g->launches;
   CK(cudaStreamSynchronize(s));
@@ -1264,8 +1274,9 @@ static int infer_batch_host_impl(DcuEngine* e, const uint8_t* frames_host, int n
   const size_t fbytes = gbytes * channels;
   *total_host = 0;
   if (n == 0) return DCU_OK;
-  if (e->use_graphs && channels == 1 && n <= e->graph_max_n && n <= e->mb1 && !e->profiling && (!use_refinenet || e->has_ref)) {
-    const int rc = infer_small_graph(e, frames_host, n, dust_bin_ids, use_refinenet, counts_host, offsets_host, total_host, kpts_host,
+  if (channels == 3 && e->bgr.p == nullptr) CK(e->bgr.alloc((size_t)e->cfg.max_batch * e->cfg.height * e->cfg.width * 3));
+  if (e->use_graphs && n <= e->graph_max_n && n <= e->mb1 && !e->profiling && (!use_refinenet || e->has_ref)) {
+    const int rc = infer_small_graph(e, frames_host, n, channels, dust_bin_ids, use_refinenet, counts_host, offsets_host, total_host, kpts_host,
                                      refined_host, s);
     if (rc != 1) return rc;
   }

@@ -220,12 +220,14 @@ def infer_image(img: np.ndarray, dust_bin_ids: int, deepc: DeepcHandle,
                 device='cpu'):
     """Do full inference on a BGR image -- inference.py:32-70, same arguments and return value.
     `device` is accepted for signature compatibility; the work always runs on the engine's B200."""
-    import cv2
-    img_gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)                    # :40, stays on host (OpenCV fixed point)
-    keypoints = infer_batch(img_gray[None], dust_bin_ids, deepc, refinenet)[0]
+    # cv2.cvtColor(img, COLOR_BGR2GRAY) (:40) runs on the device inside the same launch sequence: OpenCV's fixed-point luma,
+    # bit-exact with cv2 (tests/test_gpu_golden.py::test_bgr_batch_equals_gray_batch)
+    assert img.ndim == 3 and img.shape[2] == 3, "infer_image expects a BGR image (H, W, 3)"
+    frame = np.ascontiguousarray(img, dtype=np.uint8)[None]
+    keypoints = infer_batch(frame, dust_bin_ids, deepc, refinenet)[0]
     if draw_pred:
         if refinenet is not None and keypoints.shape[0]:
-            raw = infer_batch(img_gray[None], dust_bin_ids, deepc, None)[0]
+            raw = infer_batch(frame, dust_bin_ids, deepc, None)[0]
             img = draw_inner_corners(img, raw[:, :2], raw[:, 2], radius=3, draw_ids=True, color=(0, 0, 255))
             img = draw_inner_corners(img, keypoints[:, :2], keypoints[:, 2], draw_ids=False, radius=1,
                                      color=(0, 255, 255))
