@@ -284,7 +284,10 @@ def main():
                           traffic=conv_traffic, traffic_source=traffic_src, launches=int(conv_n), kernel_ms_per_step=conv_ms / 2,
                           share_of_step=conv_ms / step_ms_prof if step_ms_prof else None,
                           decode_gather=dict(bound="hbm", achieved=(dec_bytes / (dec_ms / 1e3) / 1e9) if dec_ms > 0 else 0.0,
-                                             peak=peaks["hbm"], unit="GB/s", launches=int(dec_n), kernel_ms_per_step=dec_ms / 2)),
+                                             peak=peaks["hbm"], unit="GB/s", launches=int(dec_n), kernel_ms_per_step=dec_ms / 2,
+                                             note="SURVEY 8d bytes (82 logit planes + patches).  In this pipeline the per-cell arg-max is taken in "
+                                                  "the 1x1 head epilogues (DCU_ARG_HEADS), so the logits are neither written nor re-read: the "
+                                                  "kernel that is left reads 2 B per cell and gathers the patches")),
         )
         if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (the other ranks would be spinning on the barrier)
             fps, cores, done, dt = cpu_reference_fps(pool[:32], seconds_budget=15.0)

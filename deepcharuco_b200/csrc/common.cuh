@@ -60,6 +60,8 @@ struct ConvParams {
   int ksize;              // 3 (default when 0) or 1
   int cin_offset;         // first input channel inside the input tensor (multiple of 8)
   float* logits;          // [n][n_valid][hout][wout] fp32, or null
+  uint8_t* arg_out;       // 1x1 "logits" mode: [n][hout*wout] arg-max over the n_valid channels (first max wins), or null.  With logits ==
+                          // null the logits are never written: the fused pipeline decodes from the two arg-max maps (82 planes -> 2 bytes / cell)
   int n_valid;            // real output channels (the weight block is zero-padded to NT rows)
   float wscale_inv;       // tcgen05 path: 2^-s, undoes the power-of-two weight scaling of the fp16 split (1.0 otherwise)
   unsigned long long* stats;   // optional [8] cycle counters for the tcgen05 kernel's roles (profiling), may be null
@@ -119,6 +121,7 @@ struct DecodeParams {
   const float* loc; const float* ids; const uint8_t* frames; const float* lut;
   int n, H, W, h, w, n_ids1, dust_bin;
   int append;
+  const uint8_t* loc_arg; const uint8_t* ids_arg;   // when non-null: per-cell arg-max maps [n][h*w] from the head epilogues (loc / ids are not read)
   int32_t* counts; int32_t* offsets; int32_t* total; int32_t* kpts; float* patches;
   int max_patches;
   unsigned long long* scan_state;   // [max_batch] chained-scan cells

@@ -407,6 +407,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
         const int oy = c.y0 + tri * 16 + prow, ox = c.x0 + tci * 8 + pcol;
         const bool inb = (oy < p.hout) && (ox < p.wout);
         float head_sum = 0.f;
+        float arg_best = 0.f; int arg_idx = -1;          // 1x1 logits mode: running arg-max over the channels (first max wins)
 #pragma unroll 1
         for (int cc = 0; cc < NT / CW; ++cc) {
           float v[CW];
@@ -418,14 +419,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p, 
             for (int j = 0; j < CW; ++j) v[j] = (v[j] + sm[j]) * p.wscale_inv;   // main + (a_hi*w_lo + a_lo*w_hi), undo 2^s
           }
           const int ch0 = ch_base + cc * CW;
-          if (p.logits != nullptr) {
-            // detector heads: logits = acc + bias, no activation, fp32 NCHW (the layout pred_argmax reads, model_utils.py:72)
+          if (p.logits != nullptr || p.arg_out != nullptr) {
+            // detector heads: logits = acc + bias, no activation, fp32 NCHW (the layout pred_argmax reads, model_utils.py:72);
+            // arg_out: torch.argmax over the channels (model_utils.py:73-74) on exactly those values, strict '>' = first maximum
             if (inb) {
               const size_t plane_o = (size_t)p.hout * p.wout;
-              float* o = p.logits + (size_t)c.img * p.n_valid * plane_o + (size_t)oy * p.wout + ox;
+              float* o = p.logits ? p.logits + (size_t)c.img * p.n_valid * plane_o + (size_t)oy * p.wout + ox : nullptr;
 #pragma unroll
               for (int j = 0; j < CW; ++j)
-                if (ch0 + j < p.n_valid) o[(size_t)(ch0 + j) * plane_o] = v[j] + prm[ch0 + j];
+                if (ch0 + j < p.n_valid) {
+                  const float lv = v[j] + prm[ch0 + j];
+                  if (o) o[(size_t)(ch0 + j) * plane_o] = lv;
+                  if (arg_idx < 0 || lv > arg_best) { arg_best = lv; arg_idx = ch0 + j; }
+                }
+              if (p.arg_out != nullptr && cc == NT / CW - 1)
+                p.arg_out[(size_t)c.img * plane_o + (size_t)oy * p.wout + ox] = (uint8_t)arg_idx;
             }
             continue;
           }

@@ -46,7 +46,20 @@ decode_gather_kernel(DecodeParams p) {
   // with one CTA per frame.  Strict '>' keeps the FIRST maximum, as torch.argmax does.
   const float* loc = p.loc + (size_t)f * 65 * cells;
   const float* ids = p.ids + (size_t)f * p.n_ids1 * cells;
-  if ((cells & 3) == 0) {
+  if (p.loc_arg != nullptr) {
+    // the arg-maxes were taken in the 1x1 head epilogues (conv_tc.cu, on the very logit values this phase would read): 2 bytes per cell
+    const uint8_t* la_map = p.loc_arg + (size_t)f * cells;
+    const uint8_t* ia_map = p.ids_arg + (size_t)f * cells;
+    for (int c = tid; c < cells; c += D_THREADS) {
+      const int la = la_map[c];
+      const int id = (la == 64) ? p.dust_bin : (int)ia_map[c];      // model_utils.py:77
+      if (id != p.dust_bin) {                                       // model_utils.py:111
+        const int slot = atomicAdd(&s_count, 1);
+        key_u[slot] = (uint32_t)id * (uint32_t)cells + (uint32_t)c;
+        pix_u[slot] = (uint32_t)la;
+      }
+    }
+  } else if ((cells & 3) == 0) {
     const int quads = cells >> 2;
     for (int q = tid; q < quads; q += D_THREADS) {
       const float4* lp = reinterpret_cast<const float4*>(loc) + q;

@@ -325,6 +325,9 @@ struct DcuEngine {
   DevBuf stage2_in;             // conv2b output for mb2 frames (input of conv3a)
   DevBuf heads;                 // (Pa|Da) output for mb2 frames
   DevBuf loc, ids;              // [mb2] logits when the caller does not want them
+  DevBuf loc_arg, ids_arg;      // [mb2][cells] u8 arg-max maps written by the 1x1 head epilogues in the fused pipeline
+  bool arg_heads = true;        // DCU_ARG_HEADS=0: heads write fp32 logits and the decode re-reads all 82 planes
+  bool arg_heads_now = false;   // set around the fused pipeline's detector + decode
   DevBuf counts, offsets, total, kpts, patches, keys, refined, scan_state, frames;
   DevBuf pnp_obj;               // [n_obj][2] board corner table of the last solve_pnp geometry
   int pnp_cols = 0, pnp_rows = 0; double pnp_sq = 0.0;
@@ -373,7 +376,7 @@ struct DcuEngine {
     if (gstream) cudaStreamDestroy(gstream);
     if (ev_start) cudaEventDestroy(ev_start);
     for (int i = 0; i < 2; ++i) { if (ev_done[i]) cudaEventDestroy(ev_done[i]); if (ev_free[i]) cudaEventDestroy(ev_free[i]); }
-    DevBuf* all[] = {&pnp_obj, &flat8[0], &flat8[1], &flat8[2], &bgr, &c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
+    DevBuf* all[] = {&loc_arg, &ids_arg, &pnp_obj, &flat8[0], &flat8[1], &flat8[2], &bgr, &c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
                      &ids, &counts, &offsets, &total, &kpts, &patches, &keys, &refined, &scan_state, &frames};
     for (DevBuf* b : all) b->release();
     FirstLayer* fl[] = {&det_first, &ref_first};
@@ -693,6 +696,10 @@ static int detector_group(DcuEngine* e, const uint8_t* frames, const float* imag
       p.in = e->heads.as<float>(); p.bias = hd.bias.as<float>(); p.alpha = hd.ones.as<float>(); p.beta = hd.ones.as<float>();
       p.n = n; p.cin = 256; p.cout_total = hd.nt; p.hin = H / 8; p.win = W / 8; p.hout = H / 8; p.wout = W / 8;
       p.ksize = 1; p.cin_offset = which ? 256 : 0; p.logits = which ? ids : loc; p.n_valid = which ? e->cfg.n_ids + 1 : 65;
+      if (e->arg_heads_now) {       // fused pipeline: arg-max in the epilogue, logits never written (loc / ids are null then)
+        p.logits = nullptr;
+        p.arg_out = (which ? e->ids_arg : e->loc_arg).as<uint8_t>();
+      }
       p.wscale_inv = 1.0f / hd.scale; p.stats = nullptr;
       int tr, tc;
       tc_tile_arrangement(hd.nt, p.hout, p.wout, &tr, &tc);
@@ -725,11 +732,13 @@ static int decode_group(DcuEngine* e, const float* loc, const float* ids, const 
                         cudaStream_t s) {
   DecodeParams d{};
   d.loc = loc; d.ids = ids; d.frames = frames; d.lut = e->lut.as<float>();
+  if (e->arg_heads_now) { d.loc_arg = e->loc_arg.as<uint8_t>(); d.ids_arg = e->ids_arg.as<uint8_t>(); }
   d.n = n; d.H = e->cfg.height; d.W = e->cfg.width; d.h = d.H / 8; d.w = d.W / 8; d.n_ids1 = e->cfg.n_ids + 1;
   d.dust_bin = dust_bin; d.append = append; d.counts = counts; d.offsets = offsets; d.total = total; d.kpts = kpts;
   d.patches = patches; d.max_patches = e->cfg.max_patches; d.scan_state = e->scan_state.as<unsigned long long>();
   d.epoch = e->epoch_override ? e->epoch_override : e->epoch++;
   // algorithmic bytes: logits read once; + K*(2304 read + 2304 written + 16) added by the caller's K
+  // with the arg-max taken in the head epilogues the kernel that is left is still reported against these bytes
   e->prof_begin(3, (double)(65 + d.n_ids1) * d.h * d.w * 4.0 * n, s);
   launch_decode_gather(d, s);
   e->prof_end(s);
@@ -926,6 +935,9 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   TRYC(e->act[1].alloc(act_floats * 4));
   TRYC(e->stage2_in.alloc((size_t)e->mb2 * 64 * (H / 4) * (W / 4) * 4));
   TRYC(e->heads.alloc((size_t)e->mb2 * 512 * (H / 8) * (W / 8) * 4));
+  TRYC(e->loc_arg.alloc((size_t)e->mb2 * (H / 8) * (W / 8)));
+  TRYC(e->ids_arg.alloc((size_t)e->mb2 * (H / 8) * (W / 8)));
+  if (const char* v = getenv("DCU_ARG_HEADS")) e->arg_heads = atoi(v) != 0;
   TRYC(e->loc.alloc((size_t)e->mb2 * 65 * (H / 8) * (W / 8) * 4));
   TRYC(e->ids.alloc((size_t)e->mb2 * (cfg->n_ids + 1) * (H / 8) * (W / 8) * 4));
   TRYC(e->counts.alloc((size_t)cfg->max_batch * 4));
@@ -1126,10 +1138,13 @@ int dcu_infer_batch(DcuEngine* e, const uint8_t* frames_dev, int n, int dust_bin
     const int m = std::min(e->mb2, n - f0);
     const uint8_t* fr = frames_dev + (size_t)f0 * H * W;
     e->h2d_base = f0 / e->mb1;
-    if ((rc = detector_group(e, fr, nullptr, m, e->loc.as<float>(), e->ids.as<float>(), s))) return rc;
-    if ((rc = decode_group(e, e->loc.as<float>(), e->ids.as<float>(), fr, m, dust_bin_ids, f0 > 0, counts_dev + f0,
-                           offsets_dev + f0, total_dev, kpts_dev, use_refinenet ? e->patches.as<float>() : nullptr, s)))
-      return rc;
+    e->arg_heads_now = e->arg_heads && e->conv_impl == DCU_CONV_TCGEN05 && e->cfg.n_ids + 1 <= 64;
+    rc = detector_group(e, fr, nullptr, m, e->loc.as<float>(), e->ids.as<float>(), s);
+    if (rc == DCU_OK)
+      rc = decode_group(e, e->loc.as<float>(), e->ids.as<float>(), fr, m, dust_bin_ids, f0 > 0, counts_dev + f0,
+                        offsets_dev + f0, total_dev, kpts_dev, use_refinenet ? e->patches.as<float>() : nullptr, s);
+    e->arg_heads_now = false;
+    if (rc) return rc;
   }
   if (!use_refinenet) return DCU_OK;
   CK(cudaMemcpyAsync(e->h_total, total_dev, 4, cudaMemcpyDeviceToHost, s));
@@ -1202,12 +1217,14 @@ static int infer_small_graph(DcuEngine* e, const uint8_t* frames_host, int n, in
     } else {
       ce = cudaMemcpyAsync(e->frames.p, e->h_frames, (size_t)n * H * W, cudaMemcpyHostToDevice, gs);
     }
+    e->arg_heads_now = e->arg_heads && e->conv_impl == DCU_CONV_TCGEN05 && e->cfg.n_ids + 1 <= 64;
     if (ce == cudaSuccess) rc = detector_group(e, e->frames.as<uint8_t>(), nullptr, n, e->loc.as<float>(), e->ids.as<float>(), gs);
     if (ce == cudaSuccess && rc == DCU_OK) ce = cudaMemsetAsync(e->scan_state.p, 0, (size_t)n * 8, gs);
     if (ce == cudaSuccess && rc == DCU_OK)
       rc = decode_group(e, e->loc.as<float>(), e->ids.as<float>(), e->frames.as<uint8_t>(), n, dust_bin_ids, 0, e->counts.as<int32_t>(),
                         e->offsets.as<int32_t>(), e->total.as<int32_t>(), e->kpts.as<int32_t>(),
                         use_refinenet ? e->patches.as<float>() : nullptr, gs);
+    e->arg_heads_now = false;
     if (ce == cudaSuccess && rc == DCU_OK && use_refinenet)
       rc = refine_run(e, e->patches.as<float>(), e->kpts.as<int32_t>(), 4, pfix, nullptr, e->refined.as<float>(), nullptr, gs);
     if (ce == cudaSuccess && rc == DCU_OK) ce = cudaMemcpyAsync(e->h_total, e->total.p, 4, cudaMemcpyDeviceToHost, gs);
