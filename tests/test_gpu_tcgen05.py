@@ -124,3 +124,20 @@ def test_fused_first_layer_is_bit_identical(states, golden_synth, monkeypatch):
         for a, b in zip(outs["1"], outs["0"]):
             assert np.array_equal(a, b)
         assert np.array_equal(outs["1"][0], outs["1"][2])          # u8 entry == fp32 entry
+
+
+def test_argmax_heads_equal_logit_decode(states, monkeypatch):
+    """Fused pipeline with the per-cell arg-max taken in the 1x1 head epilogues (default) vs heads that write fp32 logits which the
+    decode kernel re-reads (DCU_ARG_HEADS=0): the arg-max is taken on the same values, so every result row is identical."""
+    frames = synth.make_frames(40, 240, 320, seed=17)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DCU_ARG_HEADS", mode)
+        e = N.Engine(states[0], states[1], 240, 320, 16, 0, max_batch=40, max_patches=4096)
+        try:
+            outs[mode] = [a.copy() if a is not None else None for a in e.infer_batch_host(frames, 16, True)]
+        finally:
+            e.close()
+    for a, b in zip(outs["1"], outs["0"]):
+        assert np.array_equal(a, b)
+    assert outs["1"][0].sum() > 100          # the frames do contain corners
