@@ -1,1 +1,3 @@
-(timeout 600 python -m pytest tests/test_gpu_tcgen05.py -m gpu -x -q -k "argmax_heads" 2>&1 | tail -3)
+python tools/bench_configs.py --iters 5 --out gpurun_out/r1h_configs.json > gpurun_out/r1h_configs.log 2>&1; python -c "
+import json; d=json.load(open('gpurun_out/r1h_configs.json'))
+for k,v in d.items(): print(k, {a: (round(b,3) if isinstance(b,float) else b) for a,b in v.items()})"
