@@ -297,7 +297,7 @@ struct DcuEngine {
   DevBuf ref_head_w; float ref_head_b = 0.f;
 
   DevBuf lut;                   // [256] (x-128)/255
-  int mb1 = 32, mb2 = 256, rp = 4096;   // micro-batch sizes: full-res layers, low-res layers, RefineNet patches
+  int mb1 = 64, mb2 = 256, rp = 4096;   // micro-batch sizes: full-res layers, low-res layers, RefineNet patches
   int rp_plain = 1024;                  // RefineNet chunk when the upsampled tensors are materialised
   DevBuf act[2];                // ping-pong activation buffers
   DevBuf c1[2];                 // conv1a outputs, double-buffered: conv1a of micro-batch i+1 (HBM-write bound, side stream)
@@ -889,7 +889,7 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   const double area = (double)H * W / (320.0 * 240.0);
   // Sized for wave efficiency, not L2 residency: at the tensor-bound rate the activation traffic is a few hundred
   // GB/s, far below HBM bandwidth, while a launch with few tiles leaves most of the 148 SMs idle in its last wave.
-  e->mb1 = std::max(1, (int)std::floor(32.0 / area + 1e-9));
+  e->mb1 = std::max(1, (int)std::floor(64.0 / area + 1e-9));       // 64 frames at 320x240: +1.3 % over 32 (fewer launches and tails)
   e->mb2 = std::max(e->mb1, (int)std::floor(256.0 / area + 1e-9));
   e->mb1 = std::min(e->mb1, std::max(1, cfg->max_batch));
   e->mb2 = std::min(e->mb2, std::max(e->mb1, cfg->max_batch));
