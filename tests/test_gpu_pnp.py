@@ -44,10 +44,10 @@ def test_pnp_batch_matches_cv2(models, golden_sample, golden_synth):
             assert ret and want[0] and rvec.shape == (3, 1) and rvec.dtype == np.float64
             if kp.shape[0] < 6:
                 continue        # 4-5 coplanar points: the pose is ambiguous, cv2 and any other solver may pick different minima
-            # never a worse minimum of the same cost than cv2; same pose to 1e-3 (1e-6 when cv2's 20 LM steps converge)
+            # never a worse minimum of the same cost than cv2; same pose to 1e-5 (CPU run of the same core: max 8e-8)
             assert _rms(kp, rvec, tvec, K_CAM, d) <= _rms(kp, want[1], want[2], K_CAM, d) * (1 + 1e-6) + 1e-9
             err = max(np.abs(rvec - want[1]).max(), np.abs(tvec - want[2]).max())
-            assert err <= 1e-3, err
+            assert err <= 1e-5, err
             tight += err <= 1e-6
         assert tight >= len([r for r in rows if r.size and r.shape[0] >= 6]) // 2
 
@@ -76,9 +76,9 @@ def test_pnp_on_device_results_and_throughput(models):
         errs.append(max(np.abs(rvec[i] - w[1].ravel()).max(), np.abs(tvec[i] - w[2].ravel()).max()))
     errs = np.sort(np.array(errs))
     print("PNP |pose - cv2| over %d frames: median %.2e, 90%% %.2e, max %.2e" % (len(errs), np.median(errs), errs[int(0.9 * len(errs))], errs[-1]))
-    # cv2 stops after 20 LM steps whether or not it has converged (close, strongly foreshortened boards): those frames agree
-    # to ~1e-3, the rest to ~1e-7
-    assert len(errs) >= 16 and np.median(errs) <= 1e-6 and errs[-1] <= 2e-2
+    # cv2 stops after 20 LM steps whether or not it has converged; with the same start (refined homography) the trajectories
+    # coincide, so even those frames agree
+    assert len(errs) >= 16 and np.median(errs) <= 1e-8 and errs[-1] <= 1e-4
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(20):

@@ -71,10 +71,10 @@ def test_golden_frames_match_cv2(checker, golden_synth):
     for (kp, cam, d, *_), (r, rv, tv) in zip(cases, got):
         ret, rvec, tvec = dc.solve_pnp(kp, 5, 5, 0.01, cam, d)
         assert ret and r == 1
-        # same cost function, equivalent start: never a worse minimum than cv2's, and the same pose to 1e-3
-        # (agreement is ~1e-8 when cv2's 20 LM steps converge; a far, small board leaves both short of the minimum)
+        # same cost function, same start (normalised DLT + refined homography), same damping schedule: never a worse minimum than
+        # cv2's and the same pose to 1e-6 (measured: median 7e-15, max 8e-8 over these 48 cases)
         assert reproj_rms(kp, rv, tv, cam, d) <= reproj_rms(kp, rvec, tvec, cam, d) * (1 + 1e-6) + 1e-9
-        assert np.abs(rv - rvec.ravel()).max() <= 1e-3 and np.abs(tv - tvec.ravel()).max() <= 1e-3
+        assert np.abs(rv - rvec.ravel()).max() <= 1e-6 and np.abs(tv - tvec.ravel()).max() <= 1e-6
 
 
 def test_few_points_and_bad_ids(checker, golden_sample):
