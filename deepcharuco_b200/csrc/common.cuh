@@ -183,6 +183,9 @@ struct MetricsParams {
   float* l2; float* ratio; int32_t* valid;                      // [n]
 };
 void launch_dc_metrics(const MetricsParams& p, cudaStream_t s);
+// per sample |argmax(pred) - argmax(target)|_2 over h x w maps; pred == null: the predicted arg-max comes from pred_corners (col, row)
+void launch_heat_argmax_dist(const float* pred, const int32_t* pred_corners, const float* target, int p, int h, int w, float* dist,
+                             cudaStream_t s);
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

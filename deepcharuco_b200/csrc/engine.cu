@@ -1384,6 +1384,17 @@ int dcu_dc_metrics(DcuEngine* e, const int32_t* counts_dev, const int32_t* offse
   return DCU_OK;
 }
 
+int dcu_refinenet_metrics(DcuEngine* e, const float* heat_pred_dev, const int32_t* corners_pred_dev, const float* heat_target_dev, int p,
+                          float* dist_dev, void* stream) {
+  if (!e || (!heat_pred_dev && !corners_pred_dev) || !heat_target_dev || !dist_dev || p < 0)
+    return fail(DCU_ERR_INVALID, "dcu_refinenet_metrics: bad argument");
+  CK(cudaSetDevice(e->cfg.device));
+  launch_heat_argmax_dist(heat_pred_dev, corners_pred_dev, heat_target_dev, p, 64, 64, dist_dev, (cudaStream_t)stream);
+  if (p > 0) e->launches++;
+  CK(cudaGetLastError());
+  return DCU_OK;
+}
+
 // ---- batched solve_pnp (inference.py:15-29) ----
 static int pnp_object_table(DcuEngine* e, int col_count, int row_count, double square_len) {
   // object_points[:, :2] = meshgrid(arange(1,row_count), arange(1,col_count)).reshape(2,-1).T * square_len  (float32 storage):

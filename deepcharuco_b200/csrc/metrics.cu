@@ -66,7 +66,62 @@ dc_metrics_kernel(MetricsParams p) {
   }
 }
 
+// Refinenet_Metrics.update (models/metrics.py:141-158): per sample the L2 distance, in heat-map pixels, between the arg-max of the
+// predicted heat map and the arg-max of the target map (torch.argmax of the flattened map: first maximum).  One CTA per sample;
+// every thread scans a strided slice keeping (value, lowest index), then a shared-memory tree reduction with the same tie rule.
+constexpr int R_THREADS = 256;
+
+__device__ __forceinline__ void argmax_merge(float& v, int& i, float ov, int oi) {
+  if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+
+__global__ void __launch_bounds__(R_THREADS)
+heat_argmax_dist_kernel(const float* __restrict__ pred, const int32_t* __restrict__ pred_corners, const float* __restrict__ target,
+                        int hw, int w, float* __restrict__ dist) {
+  __shared__ float sv[2][R_THREADS];
+  __shared__ int si[2][R_THREADS];
+  const int f = blockIdx.x, tid = threadIdx.x;
+  for (int which = 0; which < 2; ++which) {
+    const float* src = which ? target + (size_t)f * hw : (pred ? pred + (size_t)f * hw : nullptr);
+    float bv = 0.f; int bi = 0x7fffffff;
+    if (src != nullptr)
+      for (int i = tid; i < hw; i += R_THREADS) {
+        const float v = src[i];
+        if (bi == 0x7fffffff || v > bv) { bv = v; bi = i; }          // ascending i: strict '>' keeps the first maximum of this slice
+      }
+    sv[which][tid] = bv; si[which][tid] = bi;
+  }
+  __syncthreads();
+  for (int s = R_THREADS / 2; s >= 1; s >>= 1) {
+    if (tid < s)
+      for (int which = 0; which < 2; ++which) {
+        float v = sv[which][tid]; int i = si[which][tid];
+        const int oi = si[which][tid + s];
+        if (oi != 0x7fffffff) {
+          if (i == 0x7fffffff) { v = sv[which][tid + s]; i = oi; }
+          else argmax_merge(v, i, sv[which][tid + s], oi);
+        }
+        sv[which][tid] = v; si[which][tid] = i;
+      }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int pr, pc;
+    if (pred != nullptr) { pr = si[0][0] / w; pc = si[0][0] - pr * w; }
+    else { pc = pred_corners[2 * f]; pr = pred_corners[2 * f + 1]; }     // (col, row) as RefineNet.infer_patches returns them
+    const int tr = si[1][0] / w, tc = si[1][0] - tr * w;
+    const float dr = (float)(pr - tr), dc = (float)(pc - tc);
+    dist[f] = __fsqrt_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(dc, dc)));
+  }
+}
+
 }  // namespace
+
+void launch_heat_argmax_dist(const float* pred, const int32_t* pred_corners, const float* target, int p, int h, int w, float* dist,
+                             cudaStream_t s) {
+  if (p <= 0) return;
+  heat_argmax_dist_kernel<<<p, R_THREADS, 0, s>>>(pred, pred_corners, target, h * w, w, dist);
+}
 
 void launch_dc_metrics(const MetricsParams& p, cudaStream_t s) {
   if (p.n <= 0) return;

@@ -78,3 +78,57 @@ class DC_Metrics:
     def compute(self):
         """metrics.py:131-132."""
         return self.distance, self.ratio
+
+
+class Refinenet_Metrics:
+    """Mirror of /root/reference/src/models/metrics.py:135-161 with the per-sample arg-maxes and distances on the device
+    (`dcu_refinenet_metrics`).  `update(preds, target)`: preds (N,1,64,64) or (N,64,64) heat maps, target (N,64,64) -- as the
+    reference; `update_patches(patches, keypoints, target)`: runs the engine's own RefineNet on (N,24,24) patches and compares its
+    arg-max with the target's."""
+    higher_is_better = False
+
+    def __init__(self, refinenet):
+        self._ctx = refinenet._ctx
+        self.distance = np.float32(0.0)
+
+    def _run(self, eng, heat_pred, corners, target):
+        import torch
+        dev = torch.device("cuda", eng.device)
+        target = torch.as_tensor(target).to(device=dev, dtype=torch.float32).contiguous()
+        n = int(target.shape[0])
+        assert tuple(target.shape[1:]) == (64, 64), "targets must be (N, 64, 64) heat maps"
+        dist = torch.empty(n, dtype=torch.float32, device=dev)
+        s = torch.cuda.current_stream(dev).cuda_stream
+        N.check(N.lib().dcu_refinenet_metrics(eng.handle, None if heat_pred is None else heat_pred.data_ptr(),
+                                              None if corners is None else corners.data_ptr(), target.data_ptr(), n, dist.data_ptr(), s))
+        d = dist.cpu().numpy()
+        if n:
+            self.distance = np.float32(self.distance + d.mean(dtype=np.float32))       # metrics.py:157-158
+        return d
+
+    def update(self, preds, target):
+        import torch
+        eng = next(iter(self._ctx._engines.values())) if self._ctx._engines else self._ctx.engine(240, 320)
+        dev = torch.device("cuda", eng.device)
+        preds = torch.as_tensor(preds).to(device=dev, dtype=torch.float32)
+        if preds.ndim == 4:
+            preds = preds[:, 0]                                                        # loc_x.squeeze(1), metrics.py:143
+        return self._run(eng, preds.contiguous(), None, target)
+
+    def update_patches(self, patches, keypoints, target):
+        import torch
+        eng = next(iter(self._ctx._engines.values())) if self._ctx._engines else self._ctx.engine(240, 320)
+        dev = torch.device("cuda", eng.device)
+        patches = torch.as_tensor(patches).to(device=dev, dtype=torch.float32).reshape(-1, 24, 24).contiguous()
+        n = int(patches.shape[0])
+        if n > eng.max_patches:
+            eng = self._ctx.engine(eng.height, eng.width, max_batch=eng.max_batch, max_patches=n)
+        kp = torch.as_tensor(np.asarray(keypoints)).to(device=dev, dtype=torch.int32).reshape(-1, 2).contiguous()
+        corners = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        refined = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        s = torch.cuda.current_stream(dev).cuda_stream
+        N.check(N.lib().dcu_refine_forward(eng.handle, patches.data_ptr(), kp.data_ptr(), 2, n, corners.data_ptr(), refined.data_ptr(), None, s))
+        return self._run(eng, None, corners, target)
+
+    def compute(self):
+        return self.distance

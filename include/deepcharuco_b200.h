@@ -184,6 +184,14 @@ int dcu_dc_metrics(DcuEngine* e, const int32_t* counts_dev, const int32_t* offse
                    const int64_t* loc_target_dev, const int64_t* ids_target_dev, int dust_bin_ids, float* l2_dev,
                    float* ratio_dev, int32_t* valid_dev, void* stream);
 
+/* RefineNet validation metric on the device: the per-sample part of Refinenet_Metrics.update (models/metrics.py:141-158):
+ * dist[i] = L2 distance in heat-map pixels between the arg-max of the predicted 64x64 heat map and the arg-max of the target map
+ * (first maximum of the flattened map).  The prediction is either a heat map tensor heat_pred_dev [p][64][64] or, when that is
+ * NULL, the (col, row) arg-maxes corners_pred_dev [p][2] that dcu_refine_forward already produced.  The caller accumulates
+ * distance += mean(dist) like the reference. */
+int dcu_refinenet_metrics(DcuEngine* e, const float* heat_pred_dev, const int32_t* corners_pred_dev, const float* heat_target_dev, int p,
+                          float* dist_dev, void* stream);
+
 /* Select the 3x3 conv implementation after creation (DCU_CONV_*). */
 int dcu_set_conv_impl(DcuEngine* e, int conv_impl);
 

@@ -77,3 +77,27 @@ class DCMetrics:
 
     def compute(self):
         return self.distance, self.ratio
+
+
+class RefinenetMetrics:
+    """metrics.py:135-161 -- per update: mean over the batch of the L2 distance (in heat-map pixels) between the arg-max of the
+    predicted 64x64 heat map and the arg-max of the target map (first maximum of the flattened map, like torch.argmax)."""
+
+    def __init__(self):
+        self.distance = np.float32(0)
+
+    @staticmethod
+    def per_sample(preds, target):
+        p = np.asarray(preds, np.float32).reshape(len(preds), -1)
+        t = np.asarray(target, np.float32).reshape(len(target), -1)
+        d = np.int64(np.asarray(target).shape[-1])
+        mp, mt = p.argmax(1), t.argmax(1)
+        a = np.stack((mp // d, mp % d), 1).astype(np.float32)
+        b = np.stack((mt // d, mt % d), 1).astype(np.float32)
+        return np.sqrt(((a - b) ** 2).sum(1, dtype=np.float32)).astype(np.float32)
+
+    def update(self, preds, target):
+        self.distance = np.float32(self.distance + self.per_sample(preds, target).mean(dtype=np.float32))
+
+    def compute(self):
+        return self.distance

@@ -7,7 +7,7 @@ import torch
 import deepcharuco_b200 as dc
 import oracle
 from conftest import load_golden
-from deepcharuco_b200.metrics import DC_Metrics
+from deepcharuco_b200.metrics import DC_Metrics, Refinenet_Metrics
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-6      # fp32: per-id distances are bit-exact (integer coordinates); only the order of the final sums differs
@@ -50,3 +50,29 @@ def test_update_frames_end_to_end(models, golden_synth):
     o = oracle.metrics.DCMetrics(16)
     o.update((_one_hot(g["loc_argmax"], 65).cpu().numpy(), _one_hot(g["ids_argmax"], 17).cpu().numpy()), (g["loc_target"], g["ids_target"]))
     assert np.allclose(m.compute(), o.compute(), rtol=TOL, atol=TOL)
+
+
+def test_refinenet_metrics_match_reference(models, golden_synth):
+    """Refinenet_Metrics on the device against the reference's own class (tests/golden/refinenet_metrics_seed0.npz): heat-map inputs
+    like the reference's update(), and the engine's own RefineNet on the golden patches (its arg-max may differ from the reference's
+    on at most the one near-tie patch of the golden set)."""
+    r = load_golden("refinenet_metrics_seed0.npz")
+    heat = golden_synth["heat"]
+    p = heat.shape[0]
+    target = np.stack([np.roll(heat[i], (int(r["shifts"][i, 0]), int(r["shifts"][i, 1])), axis=(0, 1)) for i in range(p)])
+    m = Refinenet_Metrics(models[1])
+    d = m.update(torch.from_numpy(heat[:, None]).cuda(), target)
+    assert np.array_equal(d, r["per_dist"])                       # integer arg-max positions: the fp32 distances are bit-exact
+    assert np.allclose(m.compute(), r["after_update1"], rtol=TOL)
+    m.update(heat[5:20, None], target[5:20])
+    assert np.allclose(m.compute(), r["after_update2"], rtol=TOL)
+    # first-maximum tie rule on a flat map, and a maximum in the last element
+    flat = np.zeros((2, 64, 64), np.float32); flat[1, 63, 63] = 1.0
+    tgt = np.zeros((2, 64, 64), np.float32); tgt[0, 3, 4] = 1.0; tgt[1, 63, 63] = 2.0
+    d2 = Refinenet_Metrics(models[1]).update(flat, tgt)
+    assert np.array_equal(d2, np.array([5.0, 0.0], np.float32))
+    m2 = Refinenet_Metrics(models[1])
+    d3 = m2.update_patches(golden_synth["patches"], golden_synth["kpts"][:p], target)
+    assert (d3 != r["per_dist"]).sum() <= 1
+    want = oracle.metrics.RefinenetMetrics.per_sample(heat, target)
+    assert (d3 != want).sum() <= 1

@@ -24,3 +24,21 @@ def test_metrics_oracle_matches_reference():
     assert np.allclose(m.compute(), g["after_update1"], rtol=1e-6, atol=1e-6)
     m.update((loc_hat[3:8], ids_hat[3:8]), (g["loc_target"][3:8], g["ids_target"][3:8]))
     assert np.allclose(m.compute(), g["after_update2"], rtol=1e-6, atol=1e-6)
+
+
+def _refinenet_case():
+    g = load_golden("synthetic_320x240_seed0.npz")
+    r = load_golden("refinenet_metrics_seed0.npz")
+    heat = g["heat"]
+    target = np.stack([np.roll(heat[i], (int(r["shifts"][i, 0]), int(r["shifts"][i, 1])), axis=(0, 1)) for i in range(len(heat))])
+    return heat, target, r
+
+
+def test_refinenet_metrics_oracle_matches_reference():
+    heat, target, r = _refinenet_case()
+    m = oracle.metrics.RefinenetMetrics()
+    assert np.allclose(m.per_sample(heat, target), r["per_dist"], rtol=1e-6, atol=1e-6)
+    m.update(heat[:, None], target)
+    assert np.allclose(m.compute(), r["after_update1"], rtol=1e-6)
+    m.update(heat[5:20, None], target[5:20])
+    assert np.allclose(m.compute(), r["after_update2"], rtol=1e-6)

@@ -74,6 +74,28 @@ def main():
                         meta=np.array("reference metrics.py DC_Metrics(16), torch " + torch.__version__))
     print("per-sample l2:", np.round(per_l2, 3)); print("per-sample ratio:", np.round(per_ratio, 3)); print(d1, r1, float(d2), float(r2))
 
+    # --- Refinenet_Metrics (metrics.py:135-161): predictions = the reference RefineNet's heat maps of the golden patches, targets =
+    # the same maps rolled by a few pixels (stored as the shifts only; tests rebuild them), so arg-max positions differ by known amounts
+    heat = torch.from_numpy(g["heat"])                                  # (P, 64, 64)
+    P = heat.shape[0]
+    shifts = rng.integers(-6, 7, size=(P, 2))
+    shifts[::5] = 0                                                     # some exact hits
+    target = torch.stack([torch.roll(heat[i], (int(shifts[i, 0]), int(shifts[i, 1])), dims=(0, 1)) for i in range(P)])
+    rm = M.Refinenet_Metrics()
+    per = []
+    for i in range(P):
+        one = M.Refinenet_Metrics()
+        one.update(heat[i:i + 1, None], target[i:i + 1])
+        per.append(float(one.compute()))
+    rm.update(heat[:, None], target)
+    u1 = float(rm.compute())
+    rm.update(heat[5:20, None], target[5:20])
+    u2 = float(rm.compute())
+    np.savez_compressed(os.path.join(OUT, "refinenet_metrics_seed0.npz"), shifts=shifts.astype(np.int64), per_dist=np.array(per, np.float32),
+                        after_update1=np.float32(u1), after_update2=np.float32(u2),
+                        meta=np.array("reference metrics.py Refinenet_Metrics on tests/golden/synthetic_320x240_seed0.npz heat maps, torch " + torch.__version__))
+    print("refinenet metric:", u1, u2, np.round(per[:8], 3))
+
 
 if __name__ == "__main__":
     main()
