@@ -85,3 +85,22 @@ def test_few_points_and_bad_ids(checker, golden_sample):
     assert [g[0] for g in got] == [0, 0, 0, 1]                     # < 4 corners -> (False, None, None), inference.py:16-17
     assert all(np.all(g[1] == 0) and np.all(g[2] == 0) for g in got[:3])
     assert np.all(np.isfinite(got[3][1])) and np.all(np.isfinite(got[3][2]))
+
+
+def test_degenerate_inputs_terminate_with_finite_or_rejected_results(checker):
+    """Collinear corners, coincident pixels, repeated ids, random garbage, absurd distortion: the solver must terminate and
+    return either ret = 0 (zeros) or a finite pose -- never NaN / inf (cv2 itself returns arbitrary poses on such input)."""
+    rng = np.random.default_rng(0)
+    cases = [(np.array([[100 + 20 * i, 80 + 5 * i, i] for i in range(4)], float), K_CAM, np.zeros(5), 5, 5, 0.01),
+             (np.array([[100, 100, i] for i in range(6)], float), K_CAM, np.zeros(5), 5, 5, 0.01),
+             (np.array([[100 + 7 * i, 90 + 3 * i, i % 3] for i in range(8)], float), K_CAM, np.zeros(5), 5, 5, 0.01)]
+    for _ in range(20):
+        k = int(rng.integers(4, 17))
+        kp = np.stack([rng.uniform(0, 320, k), rng.uniform(0, 240, k), rng.integers(0, 16, k)], 1)
+        cases.append((kp, K_CAM, rng.normal(0, 0.3, 5), 5, 5, 0.01))
+    kp = np.stack([rng.uniform(0, 320, 12), rng.uniform(0, 240, 12), np.arange(12)], 1)
+    cases.append((kp, K_CAM, np.array([5.0, -9.0, 0.5, 0.5, 3.0]), 5, 5, 0.01))
+    for ret, rv, tv in run_checker(checker, cases):
+        assert ret in (0, 1) and np.all(np.isfinite(rv)) and np.all(np.isfinite(tv))
+        if ret == 0:
+            assert np.all(rv == 0) and np.all(tv == 0)
