@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("DCU_LIB_PATH") or os.path.join(_HERE, "libdeepcharuco
 
 DCU_OK, DCU_ERR_INVALID, DCU_ERR_CUDA, DCU_ERR_CAPACITY, DCU_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 CONV_FFMA, CONV_TCGEN05 = 0, 1
+FLAG_DECODE_ONLY = 1
 CONV_DEFAULT = CONV_TCGEN05   # tcgen05 tensor-core path (fp16 hi/lo split); CONV_FFMA is the strict-fp32 CUDA-core path
 
 EXPORTS = [
@@ -147,20 +148,27 @@ class Engine:
     """One C engine: fixed (device, H, W, n_ids), workspace for max_batch frames / max_patches corners."""
 
     def __init__(self, state_det, state_ref, height, width, n_ids=16, device=0, max_batch=1, max_patches=None,
-                 conv_impl=CONV_DEFAULT):
+                 conv_impl=CONV_DEFAULT, decode_only=False):
         L = lib()
         if max_patches is None:
             max_patches = max(256, 64 * max_batch)
         self.cfg = DcuConfig(device=int(device), height=int(height), width=int(width), n_ids=int(n_ids),
-                             max_batch=int(max_batch), max_patches=int(max_patches), conv_impl=int(conv_impl), reserved=0)
-        det, keep_d = layer_table(state_det, DET_LAYERS)
+                             max_batch=int(max_batch), max_patches=int(max_patches), conv_impl=int(conv_impl),
+                             reserved=FLAG_DECODE_ONLY if decode_only else 0)
+        self.decode_only = bool(decode_only)
+        if decode_only:          # no networks, no conv workspace: dcu_decode_gather / dcu_extract_patches on caller-owned buffers
+            det, keep_d, n_det = None, [], 0
+            state_ref = None
+        else:
+            det, keep_d = layer_table(state_det, DET_LAYERS)
+            n_det = len(DET_LAYERS)
         if state_ref is not None:
             ref, keep_r = layer_table(state_ref, REF_LAYERS)
             n_ref = len(REF_LAYERS)
         else:
             ref, keep_r, n_ref = None, [], 0
         h = C.c_void_p()
-        check(L.dcu_create(C.byref(self.cfg), det, len(DET_LAYERS), ref, n_ref, C.byref(h)))
+        check(L.dcu_create(C.byref(self.cfg), det, n_det, ref, n_ref, C.byref(h)))
         self._h = h
         self.height, self.width, self.n_ids = int(height), int(width), int(n_ids)
         self.max_batch, self.max_patches = int(max_batch), int(max_patches)

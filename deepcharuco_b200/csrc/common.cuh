@@ -171,6 +171,7 @@ struct PnpParams {
   const int32_t* counts; const int32_t* offsets; const int32_t* kpts; const float* refined;
   const float* obj;       // [n_obj][2] board coordinates of the inner corners (device)
   int n, n_obj;
+  int max_rows;           // rows the kpts / refined buffers hold: a frame whose rows were dropped at capacity (decode_gather) is cut there
   int32_t* ret; double* rvec; double* tvec;     // [n], [n][3], [n][3]
 };
 void launch_pnp_batch(const PnpParams& q, const double* camera9, const double* dist, int n_dist, cudaStream_t s);
@@ -180,6 +181,7 @@ struct MetricsParams {
   const int32_t* counts; const int32_t* offsets; const int32_t* kpts;
   const long long* loc_target; const long long* ids_target;     // [n][h][w] int64, as the reference's dataset yields them
   int n, h, w, dust_bin;
+  int max_rows;                                                 // rows the kpts buffer holds (counts / offsets may point beyond: clamped)
   float* l2; float* ratio; int32_t* valid;                      // [n]
 };
 void launch_dc_metrics(const MetricsParams& p, cudaStream_t s);

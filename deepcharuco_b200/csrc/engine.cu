@@ -283,6 +283,7 @@ struct DcuEngine {
   int sm_count = 148;
   int conv_impl = DCU_CONV_FFMA;
   bool has_ref = false;
+  bool decode_only = false;     // DCU_FLAG_DECODE_ONLY: no networks, no conv workspace (pred_to_keypoints / extract_patches helpers)
   int64_t launches = 0;
 
   // detector
@@ -812,7 +813,9 @@ const char* dcu_version(void) { return "deepcharuco_b200 0.1 (sm_100a)"; }
 
 int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const DcuConvLayer* R, int n_ref,
                DcuEngine** out) {
-  if (!cfg || !D || !out || n_det != 12) return fail(DCU_ERR_INVALID, "dcu_create: need 12 detector layers");
+  if (!cfg || !out) return fail(DCU_ERR_INVALID, "dcu_create: null argument");
+  const bool decode_only = (cfg->reserved & DCU_FLAG_DECODE_ONLY) != 0;
+  if (!decode_only && (!D || n_det != 12)) return fail(DCU_ERR_INVALID, "dcu_create: need 12 detector layers");
   if (cfg->height % 8 || cfg->width % 8 || cfg->height < 24 || cfg->width < 24)
     return fail(DCU_ERR_INVALID, "dcu_create: height/width must be multiples of 8 (>= 24)");
   if (cfg->n_ids < 1 || cfg->n_ids > 30 || cfg->max_batch < 1 || cfg->max_patches < 1)
@@ -827,9 +830,23 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   e->sm_count = prop.multiProcessorCount;
   if (const char* v = getenv("DCU_SMS")) e->sm_count = std::max(2, std::min(atoi(v), prop.multiProcessorCount));   // experiments
   e->conv_impl = cfg->conv_impl;
+  e->decode_only = decode_only;
   int rc;
 #define TRY(x) do { if ((rc = (x)) != DCU_OK) { delete e; return rc; } } while (0)
 #define TRYC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { delete e; return fail(DCU_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); } } while (0)
+  if (decode_only) {
+    // decode_gather / extract_patches on caller-owned buffers only: the normalisation table and the look-back scan cells
+    std::vector<float> lut(256);
+    for (int i = 0; i < 256; ++i) lut[i] = ((float)i - 128.0f) / 255.0f;
+    TRYC(upload(e->lut, lut));
+    TRYC(e->total.alloc(16));
+    TRYC(cudaMemset(e->total.p, 0, 16));
+    TRYC(e->scan_state.alloc((size_t)cfg->max_batch * 8));
+    TRYC(cudaMemset(e->scan_state.p, 0, e->scan_state.bytes));
+    TRYC(cudaDeviceSynchronize());
+    *out = e;
+    return DCU_OK;
+  }
   // detector: conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db  (net.py:22-48)
   TRY(build_first(e->det_first, D[0], 1));
   const int pools[7] = {1, 0, 1, 0, 1, 0, 0};
@@ -1061,6 +1078,7 @@ double dcu_refine_flops_per_patch(const DcuEngine*) {
 
 int dcu_detector_forward(DcuEngine* e, const uint8_t* frames_dev, int n, float* loc_dev, float* ids_dev, void* stream) {
   if (!e || !frames_dev || !loc_dev || !ids_dev || n < 0) return fail(DCU_ERR_INVALID, "dcu_detector_forward: bad argument");
+  if (e->decode_only) return fail(DCU_ERR_INVALID, "decode-only engine: no detector");
   CK(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   const int H = e->cfg.height, W = e->cfg.width, cells = (H / 8) * (W / 8);
@@ -1075,6 +1093,7 @@ int dcu_detector_forward(DcuEngine* e, const uint8_t* frames_dev, int n, float* 
 
 int dcu_detector_forward_f32(DcuEngine* e, const float* images_dev, int n, float* loc_dev, float* ids_dev, void* stream) {
   if (!e || !images_dev || !loc_dev || !ids_dev || n < 0) return fail(DCU_ERR_INVALID, "dcu_detector_forward_f32: bad argument");
+  if (e->decode_only) return fail(DCU_ERR_INVALID, "decode-only engine: no detector");
   CK(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   const int H = e->cfg.height, W = e->cfg.width, cells = (H / 8) * (W / 8);
@@ -1128,6 +1147,7 @@ int dcu_infer_batch(DcuEngine* e, const uint8_t* frames_dev, int n, int dust_bin
   if (!e || !frames_dev || !counts_dev || !offsets_dev || !total_dev || !kpts_dev || n < 0)
     return fail(DCU_ERR_INVALID, "dcu_infer_batch: bad argument");
   if (n > e->cfg.max_batch) return fail(DCU_ERR_INVALID, "dcu_infer_batch: n > max_batch");
+  if (e->decode_only) return fail(DCU_ERR_INVALID, "decode-only engine: no detector");
   if (use_refinenet && (!e->has_ref || !refined_dev)) return fail(DCU_ERR_INVALID, "dcu_infer_batch: RefineNet not available");
   CK(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
@@ -1150,7 +1170,12 @@ int dcu_infer_batch(DcuEngine* e, const uint8_t* frames_dev, int n, int dust_bin
   CK(cudaMemcpyAsync(e->h_total, total_dev, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));   // corner count, as the reference's nonzero() does (model_utils.py:114)
   const int total = std::min(e->h_total[0], e->cfg.max_patches);
-  return refine_run(e, e->patches.as<float>(), kpts_dev, 4, total, nullptr, refined_dev, nullptr, s);
+  rc = refine_run(e, e->patches.as<float>(), kpts_dev, 4, total, nullptr, refined_dev, nullptr, s);
+  if (rc) return rc;
+  if (e->h_total[0] > e->cfg.max_patches)       // rows up to capacity are valid and refined; counts / offsets describe the full set
+    return fail(DCU_ERR_CAPACITY, "corner count " + std::to_string(e->h_total[0]) + " exceeds max_patches " +
+                                      std::to_string(e->cfg.max_patches));
+  return DCU_OK;
 }
 
 int dcu_bgr_to_gray(DcuEngine* e, const uint8_t* bgr_dev, int n, uint8_t* gray_dev, void* stream) {
@@ -1284,6 +1309,7 @@ static int infer_batch_host_impl(DcuEngine* e, const uint8_t* frames_host, int n
   if (!e || !frames_host || !counts_host || !offsets_host || !total_host || !kpts_host || n < 0)
     return fail(DCU_ERR_INVALID, "dcu_infer_batch_host: bad argument");
   if (n > e->cfg.max_batch) return fail(DCU_ERR_INVALID, "dcu_infer_batch_host: n > max_batch");
+  if (e->decode_only) return fail(DCU_ERR_INVALID, "decode-only engine: no detector");
   if (use_refinenet && !refined_host) return fail(DCU_ERR_INVALID, "dcu_infer_batch_host: refined_host is NULL");
   CK(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
@@ -1336,7 +1362,7 @@ static int infer_batch_host_impl(DcuEngine* e, const uint8_t* frames_host, int n
                            e->offsets.as<int32_t>(), e->total.as<int32_t>(), e->kpts.as<int32_t>(),
                            e->refined.as<float>(), s);
   e->h2d_active = false;
-  if (rc) return rc;
+  if (rc && rc != DCU_ERR_CAPACITY) return rc;
   int total;
   if (use_refinenet) {
     total = e->h_total[0];        // already fetched by dcu_infer_batch
@@ -1376,7 +1402,7 @@ int dcu_dc_metrics(DcuEngine* e, const int32_t* counts_dev, const int32_t* offse
   MetricsParams p{};
   p.counts = counts_dev; p.offsets = offsets_dev; p.kpts = kpts_dev;
   p.loc_target = reinterpret_cast<const long long*>(loc_target_dev); p.ids_target = reinterpret_cast<const long long*>(ids_target_dev);
-  p.n = n; p.h = e->cfg.height / 8; p.w = e->cfg.width / 8; p.dust_bin = dust_bin_ids;
+  p.n = n; p.h = e->cfg.height / 8; p.w = e->cfg.width / 8; p.dust_bin = dust_bin_ids; p.max_rows = e->cfg.max_patches;
   p.l2 = l2_dev; p.ratio = ratio_dev; p.valid = valid_dev;
   launch_dc_metrics(p, (cudaStream_t)stream);
   if (n > 0) e->launches++;
@@ -1426,7 +1452,7 @@ int dcu_solve_pnp_batch(DcuEngine* e, const int32_t* counts_dev, const int32_t* 
   if (rc) return rc;
   PnpParams q{};
   q.counts = counts_dev; q.offsets = offsets_dev; q.kpts = kpts_dev; q.refined = refined_dev;
-  q.obj = e->pnp_obj.as<float>(); q.n = n; q.n_obj = (col_count - 1) * (row_count - 1);
+  q.obj = e->pnp_obj.as<float>(); q.n = n; q.n_obj = (col_count - 1) * (row_count - 1); q.max_rows = e->cfg.max_patches;
   q.ret = ret_dev; q.rvec = rvec_dev; q.tvec = tvec_dev;
   launch_pnp_batch(q, camera_matrix9, dist_coeffs, n_dist, (cudaStream_t)stream);
   if (n > 0) e->launches++;
@@ -1489,6 +1515,7 @@ int dcu_debug_tc_stats(DcuEngine* e, int enable, uint64_t* out8) {
 int dcu_debug_conv_layer(DcuEngine* e, int net, int layer, int conv_impl, const float* in_dev, int n, int h, int w,
                          float* out_dev, void* stream) {
   if (!e || !in_dev || !out_dev || n < 1) return fail(DCU_ERR_INVALID, "dcu_debug_conv_layer: bad argument");
+  if (e->decode_only) return fail(DCU_ERR_INVALID, "decode-only engine: no networks");
   if (net == 1 && !e->has_ref) return fail(DCU_ERR_INVALID, "no RefineNet in this engine");
   CK(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;

@@ -30,7 +30,8 @@ dc_metrics_kernel(MetricsParams p) {
   const int cells = p.h * p.w;
   const long long* lt = p.loc_target + (size_t)f * cells;
   const long long* it = p.ids_target + (size_t)f * cells;
-  const int K = p.counts[f];
+  // decode_gather writes the full counts / offsets even when it dropped rows at max_patches: never read past the buffer
+  const int K = max(0, min(p.counts[f], p.max_rows - p.offsets[f]));
   const int4* rows = reinterpret_cast<const int4*>(p.kpts) + p.offsets[f];
   for (int c = tid; c < cells; c += M_THREADS) {
     const long long id = it[c];

@@ -14,8 +14,9 @@ __global__ void pnp_batch_kernel(PnpParams q, pnp::Cam cam) {
   const int f = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (f >= q.n) return;                                   // whole warp
   pnp::Pts P;
-  P.n = q.counts[f]; P.n_obj = q.n_obj; P.obj = q.obj;
   const int off = q.offsets[f];
+  // decode_gather writes the full counts / offsets even when it dropped rows at max_patches: never read past the buffer
+  P.n = max(0, min(q.counts[f], q.max_rows - off)); P.n_obj = q.n_obj; P.obj = q.obj;
   P.kp = q.kpts + 4 * (size_t)off;
   P.xy = q.refined ? q.refined + 2 * (size_t)off : nullptr;
   double rv[3], tv[3];

@@ -269,16 +269,32 @@ def pred_to_keypoints(loc_hat, ids_hat, dust_bin_ids: int):
 _SCRATCH = {}
 
 
+class _DecodeContext:
+    """Decode-only engines (no networks, no convolution workspace) for `pred_to_keypoints` / `extract_patches`, keyed by frame size."""
+
+    def __init__(self, n_ids, device):
+        self.n_ids, self.device = int(n_ids), int(device)
+        self._engines = {}
+
+    def engine(self, height, width, max_batch=1, max_patches=None) -> N.Engine:
+        key = (int(height), int(width))
+        eng = self._engines.get(key)
+        want_p = max_patches or 256
+        if eng is None or eng.max_batch < max_batch or eng.max_patches < want_p:
+            if eng is not None:
+                max_batch, want_p = max(max_batch, eng.max_batch), max(want_p, eng.max_patches)
+                eng.close()
+            eng = N.Engine(None, None, height, width, self.n_ids, self.device, max_batch=max_batch, max_patches=want_p,
+                           decode_only=True)
+            self._engines[key] = eng
+        return eng
+
+
 def _scratch_context(n_ids, device):
-    """Decode-only use (pred_to_keypoints / extract_patches) needs an engine but no particular weights."""
     key = (n_ids, device)
     if key not in _SCRATCH:
-        st = weights_io.load_state(weights_io.DEFAULT_DEEPC)
-        if n_ids != 16:
-            st = dict(st)
-            st["convDb.weight"] = np.zeros((n_ids + 1, 256, 1, 1), np.float32)
-            st["convDb.bias"] = np.zeros((n_ids + 1,), np.float32)
-        _SCRATCH[key] = _Context(st, None, n_ids, device)
+        N.lib()
+        _SCRATCH[key] = _DecodeContext(n_ids, device)
     return _SCRATCH[key]
 
 

@@ -51,7 +51,10 @@ class DC_Metrics:
         import torch
         loc_x, ids_x = preds
         n, _, h, w = loc_x.shape
-        eng = self._ctx.engine(8 * h, 8 * w, max_batch=n)
+        # early-training / random logits keep almost every cell (the reference's own metrics.py self-test): capacity = every cell.
+        # Decode + metric need no network: a decode-only engine (no conv workspace)
+        from .inference import _scratch_context
+        eng = _scratch_context(int(ids_x.shape[1]) - 1, self._ctx.device).engine(8 * h, 8 * w, max_batch=n, max_patches=n * h * w)
         dev = torch.device("cuda", eng.device)
         loc_x = loc_x.to(device=dev, dtype=torch.float32).contiguous()
         ids_x = ids_x.to(device=dev, dtype=torch.float32).contiguous()
@@ -72,7 +75,12 @@ class DC_Metrics:
         eng = self._ctx.engine(H, W, max_batch=n)
         dev = torch.device("cuda", eng.device)
         fr = torch.from_numpy(frames).to(dev)
-        o = eng.infer_batch_device(fr.data_ptr(), n, self.dust_bin_ids, False, torch.cuda.current_stream(dev).cuda_stream)
+        while True:
+            o = eng.infer_batch_device(fr.data_ptr(), n, self.dust_bin_ids, False, torch.cuda.current_stream(dev).cuda_stream)
+            total = int(o["total"].item())
+            if total <= eng.max_patches:
+                break
+            eng = self._ctx.engine(H, W, max_batch=n, max_patches=max(total, 2 * eng.max_patches))     # crowded frames: grow and retry
         return self._metrics(eng, o["counts"], o["offsets"], o["kpts"], n, target)
 
     def compute(self):

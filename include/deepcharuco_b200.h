@@ -67,8 +67,14 @@ typedef struct DcuConfig {
   int32_t max_batch;     /* frames per dcu_infer_* call (workspace is sized for this) */
   int32_t max_patches;   /* corner capacity per call, summed over the batch */
   int32_t conv_impl;     /* DCU_CONV_FFMA or DCU_CONV_TCGEN05 */
-  int32_t reserved;
+  int32_t reserved;      /* flags: DCU_FLAG_* (0 = a full engine) */
 } DcuConfig;
+
+/* DcuConfig.reserved flag: an engine without networks or convolution workspace, for the stand-alone helpers
+ * pred_to_keypoints / extract_patches (model_utils.py:81-88, :19-36 -> dcu_decode_gather / dcu_extract_patches on
+ * caller-owned buffers).  det_layers / ref_layers may be NULL; every entry point that needs a network returns
+ * DCU_ERR_INVALID. */
+#define DCU_FLAG_DECODE_ONLY 1
 
 /* Replaces inference.load_models (inference.py:73-84): builds packed device weights + workspace.
  * det_layers: 12 layers in net.py:22-48 order  (conv1a,1b,2a,2b,3a,3b,4a,4b,Pa,Pb,Da,Db);
@@ -122,7 +128,10 @@ int dcu_refine_forward(DcuEngine* e, const float* patches_dev, const int32_t* xy
  * decode) to learn the corner count -- the reference does the same at model_utils.py:114.
  * Outputs (device): counts_dev [N], offsets_dev [N], total_dev [1], kpts_dev [max_patches][4] int32
  * {x, y, id, cell} and refined_dev [max_patches][2] float, both indexed by offsets_dev[f] + j.
- * use_refinenet == 0 skips the RefineNet leg (refinenet=None, inference.py:54). */
+ * use_refinenet == 0 skips the RefineNet leg (refinenet=None, inference.py:54).
+ * More corners than max_patches: rows up to capacity are valid (and refined), counts / offsets / total describe the full set;
+ * with use_refinenet the call returns DCU_ERR_CAPACITY (it knows the count), without it the caller compares *total_dev with
+ * max_patches.  dcu_dc_metrics and dcu_solve_pnp_batch never read rows beyond max_patches. */
 int dcu_infer_batch(DcuEngine* e, const uint8_t* frames_dev, int n, int dust_bin_ids, int use_refinenet,
                     int32_t* counts_dev, int32_t* offsets_dev, int32_t* total_dev,
                     int32_t* kpts_dev, float* refined_dev, void* stream);

@@ -76,3 +76,50 @@ def test_refinenet_metrics_match_reference(models, golden_synth):
     assert (d3 != r["per_dist"]).sum() <= 1
     want = oracle.metrics.RefinenetMetrics.per_sample(heat, target)
     assert (d3 != want).sum() <= 1
+
+
+def test_dense_predictions_do_not_overrun_capacity(models):
+    """Random logits keep ~1100 of 1200 cells per frame (an untrained detector; the reference's own metrics.py self-test feeds
+    exactly this): far more than the default 64 corners per frame of an inference engine.  `update` must size the decode for every
+    cell and agree with the oracle restatement of DC_Metrics; the kernels must never read past the row buffer."""
+    rng = np.random.default_rng(11)
+    n = 6
+    loc = rng.standard_normal((n, 65, 30, 40)).astype(np.float32)
+    ids = rng.standard_normal((n, 17, 30, 40)).astype(np.float32)
+    loc_t = np.full((n, 30, 40), 64, np.int64)
+    ids_t = np.full((n, 30, 40), 16, np.int64)
+    for f in range(n):
+        cells = rng.choice(1200, 16, replace=False)
+        for i, c in enumerate(cells):
+            ids_t[f, c // 40, c % 40] = i
+            loc_t[f, c // 40, c % 40] = rng.integers(0, 64)
+    m = DC_Metrics(16, models[0])
+    l2, ratio, valid = m.update((torch.from_numpy(loc).cuda(), torch.from_numpy(ids).cuda()), (loc_t, ids_t))
+    o = oracle.metrics.DCMetrics(16)
+    o.update((loc, ids), (loc_t, ids_t))
+    assert valid.all()
+    assert np.allclose(m.compute(), o.compute(), rtol=1e-5, atol=1e-5)
+    kp, _ = oracle.pred_to_keypoints(loc, ids, 16)
+    assert kp.shape[0] > 64 * n * 10          # the case really is dense
+
+
+def test_capacity_is_an_error_not_an_overrun(states):
+    """An engine with room for 8 corners, fed frames with ~15 each: the device entry point reports DCU_ERR_CAPACITY (RefineNet leg)
+    and the metric / pose kernels stay inside the 8 rows."""
+    from deepcharuco_b200 import _native as N, synth
+    frames = synth.make_frames(4, 240, 320, seed=1)
+    e = N.Engine(states[0], states[1], 240, 320, 16, 0, max_batch=4, max_patches=8)
+    try:
+        fr = torch.from_numpy(frames).cuda()
+        with pytest.raises(N.CapacityError):
+            e.infer_batch_device(fr.data_ptr(), 4, 16, True, None)
+        o = e.infer_batch_device(fr.data_ptr(), 4, 16, False, None)
+        torch.cuda.synchronize()
+        assert int(o["total"].item()) > 8
+        ret, rvec, tvec = e.solve_pnp_batch_device(4, 5, 5, 0.01, np.array([[300., 0, 160], [0, 300., 120], [0, 0, 1]]), None, use_refined=False)
+        torch.cuda.synchronize()
+        assert ret.shape[0] == 4 and bool(torch.isfinite(rvec[ret.bool()]).all())
+        with pytest.raises(N.CapacityError):
+            e.infer_batch_host(frames, 16, True)
+    finally:
+        e.close()

@@ -19,8 +19,7 @@ def test_parity_48_frames_seed1(models, states):
     tot = parity.summarise(reps)
     print("PARITY 320x240 seed1:", tot)
     parity.assert_parity(tot)
-    flips = tot["heat_flip"] + tot["raw_px"]
-    assert flips <= max(2, tot["K"] // 200), tot          # near-tie flips are rare (fp32 ~0 / 1384)
+    parity.assert_no_flips(tot)
 
 
 def test_parity_640x480(models, states):
@@ -31,6 +30,7 @@ def test_parity_640x480(models, states):
     tot = parity.summarise([parity.compare_frame(states, f, r, w) for f, r, w in zip(frames, refined, raw)])
     print("PARITY 640x480 seed5:", tot)
     parity.assert_parity(tot)
+    parity.assert_no_flips(tot)
 
 
 @pytest.mark.parametrize("hw", [(200, 296), (24, 24), (136, 72)])
@@ -46,6 +46,7 @@ def test_parity_awkward_sizes(models, states, hw):
     tot = parity.summarise([parity.compare_frame(states, f, r, w) for f, r, w in zip(frames, refined, raw)])
     print("PARITY %dx%d:" % (W, H), tot)
     parity.assert_parity(tot)
+    parity.assert_no_flips(tot)
     # small crops rarely keep a corner, so also compare what the detector itself produces at this size
     import torch
     import oracle
@@ -58,7 +59,7 @@ def test_parity_awkward_sizes(models, states, hw):
     x = torch.from_numpy(np.stack([oracle.pre_bgr_image(f) for f in frames]))
     wl, wi = oracle.detector_forward(states[0], x)
     wl, wi = wl.numpy(), wi.numpy()
-    assert np.abs(loc.cpu().numpy() - wl).max() < 0.25 and np.abs(ids.cpu().numpy() - wi).max() < 0.25     # logits are O(100)
+    assert np.abs(loc.cpu().numpy() - wl).max() < 0.1 and np.abs(ids.cpu().numpy() - wi).max() < 0.1     # logits are O(100)
     assert np.array_equal(ids.cpu().numpy().argmax(1), wi.argmax(1))
 
 

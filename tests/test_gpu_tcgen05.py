@@ -84,7 +84,7 @@ def test_parity_tcgen05_vs_oracle(tc_models, states):
     tot = parity.summarise([parity.compare_frame(states, f, r, w) for f, r, w in zip(frames, refined, raw)])
     print("PARITY tcgen05 320x240 seed1:", tot)
     parity.assert_parity(tot)
-    assert tot["heat_flip"] + tot["raw_px"] <= max(2, tot["K"] // 200), tot
+    parity.assert_no_flips(tot)
 
 
 def test_tcgen05_deterministic_and_batch_invariant(tc_models):
@@ -98,7 +98,7 @@ def test_tcgen05_deterministic_and_batch_invariant(tc_models):
 
 
 def test_fused_first_layer_is_bit_identical(states, golden_synth, monkeypatch):
-    """conv1a computed inside conv1b's kernel (conv_tc2.cu FIRST mode, the default) vs the separate conv1a kernel + HBM round trip
+    """conv1a computed inside conv1b's kernel (conv_tc2.cu FIRST mode, DCU_FUSE_FIRST=1; off by default) vs the separate conv1a kernel + HBM round trip
     (DCU_FUSE_FIRST=0): same FMA order for conv1a, same MMAs for conv1b -> bit-identical logits, for u8 and fp32 inputs, at a
     size with ragged tiles too."""
     import torch
