@@ -159,6 +159,7 @@ cudaError_t launch_conv3x3_tc(const ConvParams& p, const float* w_blocks, int n_
 
 // CTA-pair (cta_group::2) variant, conv_tc2.cu
 int tc2_block_bytes(int nt);
+bool tc2_segmented();          // two-level accumulation on (default; DCU_SEG=0: off) -> every layer runs in 64-channel slices
 int tc2_stage_blocks(int up);       // weight blocks per bulk-copy stage (tensor-map box)
 // up != 0: p.in is the LOW-resolution tensor (hin x win) whose 2x nearest upsampling is the layer's input; hout = 2*hin
 int tc2_flat_rows(int in_row, int pad_or_up, int up);   // FLAT mode: rows of 16 pixels per halo box (tensor-map box height)

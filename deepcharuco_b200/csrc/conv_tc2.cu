@@ -82,6 +82,8 @@ struct Tc2Geo {
   // sbo = distance between consecutive groups of 8 M rows.  Standard: row_step = sbo = halo_w, a_org = 0.
   int row_step, sbo, a_org;
   int flat, tile_px, lead;     // FLAT: pixels per CTA tile (256; UP: 128), pixels loaded ahead of the tile start (multiple of 16)
+  int slice_minor;             // work items ordered tile-major (item = pair * slices + slice): the slices of one pixel tile run at the same
+                               // time on neighbouring clusters, so its halo is read from HBM once and from L2 by the other slices
   H2Layout out;                // output addressing
 };
 
@@ -270,11 +272,14 @@ __device__ __forceinline__ unsigned int orderable(float v) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
+__device__ __forceinline__ int pair_slice(long long pt, const Tc2Geo& g) {
+  return g.slice_minor ? (int)(pt % g.slices) : (int)(pt / g.pairs_per_slice);
+}
 struct Tile2 { int img, slice, y0, x0; bool valid; };       // FLAT: x0 = first pixel of the CTA tile in the run, img / y0 unused
 __device__ __forceinline__ Tile2 decode_pair_tile(long long pt, uint32_t rank, const Tc2Geo& g) {
   Tile2 c;
-  c.slice = (int)(pt / g.pairs_per_slice);
-  long long t = (pt - (long long)c.slice * g.pairs_per_slice) * 2 + rank;
+  c.slice = pair_slice(pt, g);
+  long long t = (g.slice_minor ? pt / g.slices : pt - (long long)c.slice * g.pairs_per_slice) * 2 + rank;
   c.valid = t < g.tiles_per_slice;
   if (!c.valid) t = g.tiles_per_slice - 1;            // odd tail: the peer recomputes the last tile and discards it
   if (g.flat) { c.img = 0; c.y0 = 0; c.x0 = (int)(t * g.tile_px); return c; }
@@ -287,7 +292,14 @@ __device__ __forceinline__ Tile2 decode_pair_tile(long long pt, uint32_t rank, c
 }
 
 struct NoFirst {};
-template <int NT, int KS, bool UP, bool WRES, bool FIRST, int MT_ = 2>
+// SEG (two-level accumulation).  The tensor core adds each MMA's 16 exact products to the fp32 accumulator with TRUNCATION
+// (tools/mma_probe.py): over a chain of 36 - 72 MMAs the losses are one-sided and add up coherently (measured max
+// |dloc| 0.055 on logits of +-100 against 0.0024 for an fp32 FMA chain).  In SEG mode the chain in tensor memory is ONE 16-channel
+// chunk (9 taps; 4 in UP mode): the MMA warp starts a fresh accumulator per chunk (ping-pong over the NBUF accumulator sets) and the
+// epilogue warps drain every finished chunk into fp32 registers with round-to-nearest adds while the next chunk is being issued.
+// Partial sums stay small (shorter chains lose less per step) and the register adds are unbiased.  NT = 64 only (64 running sums per
+// epilogue thread); 128-channel layers run as 64-channel slices in this mode.
+template <int NT, int KS, bool UP, bool WRES, bool FIRST, int MT_ = 2, bool SEG = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w0,
                 const __grid_constant__ CUtensorMap tmap_w1, const ConvParams p, const Tc2Geo g, const __grid_constant__ TcBn bn,
@@ -296,6 +308,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   // uniform constant loads instead of shared-memory reads (the shared-memory data pipe is what bounds this kernel).
   using Cfg = Tc2Cfg<NT, UP, WRES, MT_>;
   constexpr int MT = Cfg::MT, NBUF = Cfg::NBUF, B_STAGES = Cfg::B_STAGES;
+  static_assert(!SEG || (NT == 64 && !FIRST && NBUF >= 2), "SEG: 64-channel slices, double-buffered accumulators, one m-tile per epilogue group");
   // UP (input = 2x nearest upsampling of the tensor in HBM): per output phase (a, b) the 3x3 taps collapse to 2x2 taps on
   // the low-resolution tensor, so a weight stage is one of 2 kernel rows = 2 taps x 2 column phases (see header).
   constexpr int ROWS = UP ? 2 : KS, TPR = UP ? 2 : KS, SB = Cfg::STAGE_BLOCKS, TAPS = ROWS * SB;
@@ -491,7 +504,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     int st = 0; uint32_t ph = 0;
     for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
       if (WRES && pt != cluster_id) break;              // resident weights (one slice): loaded with the first tile only
-      const int slice = (int)(pt / g.pairs_per_slice);
+      const int slice = pair_slice(pt, g);
       const int blk0 = slice * chunks * TAPS;
       for (int blk = 0; blk < chunks * TAPS; blk += SB) {
         mbar_wait<200>(&b_empty[st], ph ^ 1u);
@@ -520,12 +533,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     int sa = 0, sb = 0, buf = 0; uint32_t pha = 0, phb = 0, phc = 0;
     for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
-      const uint32_t ph_a = UP ? (uint32_t)((pt / g.pairs_per_slice) & 1) : 0u;     // row phase of this work item
+      const uint32_t ph_a = UP ? (uint32_t)(pair_slice(pt, g) & 1) : 0u;     // row phase of this work item
       for (int q = 0; q < chunks; ++q) {
         mbar_wait(&a_full[sa], pha);
         tc_fence_after();
         const uint32_t a_hi = a_desc_lo0 + a_base0 + (uint32_t)sa * (Cfg::A_STAGE_BYTES >> 4);
-        if (q == 0) {
+        if (SEG || q == 0) {          // SEG: a fresh accumulator set per chunk
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) mbar_wait(&acc_empty[buf * MT + mt], phc ^ 1u);
           tc_fence_after();
@@ -550,25 +563,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 const uint32_t d = tmem_u + (uint32_t)((buf * MT + mt) * 2 * NT);
                 const uint32_t da_hi = a_row + (uint32_t)kx + (UP ? (uint32_t)mt : mt_off[mt]);
                 const uint32_t da_lo = da_hi + 2u * (uint32_t)halo_px;
-                umma2_f16_w(d, da_hi, a_desc_hi, b_main, b_desc_hi, IDESC_2N, (q | ky | kx) ? 1u : 0u);   // [a_hi*w_hi | a_hi*w_lo]
+                umma2_f16_w(d, da_hi, a_desc_hi, b_main, b_desc_hi, IDESC_2N, ((SEG ? 0 : q) | ky | kx) ? 1u : 0u);   // [a_hi*w_hi | a_hi*w_lo]
                 umma2_f16_w(d + NT, da_lo, a_desc_hi, b_x, b_desc_hi, IDESC_1N, 1u);                        // + a_lo*w_hi
               }
             }
             if (!WRES) umma2_commit_mc(&b_empty[sb]);
             if (ky == ROWS - 1) umma2_commit_mc(&a_empty[sa]);
-            if (ky == ROWS - 1 && q == chunks - 1) umma2_commit_mc(&acc_full[buf]);
+            if (ky == ROWS - 1 && (SEG || q == chunks - 1)) umma2_commit_mc(&acc_full[buf]);
           }
           __syncwarp();
           if (++sb == B_STAGES) { sb = 0; phb ^= 1u; }
         }
         if (++sa == Cfg::A_STAGES) { sa = 0; pha ^= 1u; }
+        if (SEG) { if (++buf == NBUF) { buf = 0; phc ^= 1u; } }
       }
-      if (++buf == NBUF) { buf = 0; phc ^= 1u; }
+      if (!SEG) { if (++buf == NBUF) { buf = 0; phc ^= 1u; } }
     }
-  } else if (warp >= 4 && (!FIRST || warp < 8)) {
+  } else if (warp >= 4 && (!FIRST || warp < 8) && (!SEG || warp < 4 + 4 * MT)) {
     // ================= epilogue (both CTAs, each drains its own 128 TMEM lanes) =================
     constexpr int CW = 16;
     const int grp = (!FIRST && warp >= 8) ? 1 : 0;       // FIRST: warps 4-7 drain both m-tiles (warps 8-11 are the conv1a producers)
+    float racc[SEG ? NT : 1];                            // SEG: this thread's running sums (one pixel x NT channels of m-tile `grp`)
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;
     const int prow = m >> 3, pcol = m & 7;
@@ -579,8 +594,30 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     asm volatile("griddepcontrol.wait;" ::: "memory");        // (ordered anyway through the activation loads; keeps the stores formally after the wait)
     for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
       const Tile2 c = decode_pair_tile(pt, rank, g);
-      mbar_wait<200>(&acc_full[buf], phc);
-      tc_fence_after();
+      if constexpr (SEG) {
+        // drain every finished chunk of m-tile `grp` into registers (RN adds), releasing its accumulator set for the chunk after next
+#pragma unroll
+        for (int j = 0; j < NT; ++j) racc[j] = 0.f;
+#pragma unroll 1
+        for (int q = 0; q < chunks; ++q) {
+          mbar_wait<40>(&acc_full[buf], phc);
+          tc_fence_after();
+#pragma unroll
+          for (int cc = 0; cc < NT / CW; ++cc) {
+            float v[CW], sm[CW];
+            const uint32_t col = (uint32_t)((buf * MT + grp) * 2 * NT + cc * CW);
+            tmem_ld16x2(tmem_base + lane_addr + col, v, tmem_base + lane_addr + col + NT, sm);
+#pragma unroll
+            for (int j = 0; j < CW; ++j) racc[cc * CW + j] += v[j] + sm[j];
+          }
+          tc_fence_before();
+          mbar_arrive_cluster(&acc_empty[buf * MT + grp], 0);      // always the leader's barrier
+          if (++buf == NBUF) { buf = 0; phc ^= 1u; }
+        }
+      } else {
+        mbar_wait<200>(&acc_full[buf], phc);
+        tc_fence_after();
+      }
       const int ch_base = (UP ? (c.slice >> 1) : c.slice) * NT;
 #pragma unroll 1
       for (int mt = grp; mt < MT; mt += (FIRST ? 1 : 2)) {
@@ -603,10 +640,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           inb = c.valid && (oy < p.hout) && (ox < p.wout);
         }
         float head_sum = 0.f;
-#pragma unroll 1
+#pragma unroll (SEG ? NT / CW : 1)
         for (int cc = 0; cc < NT / CW; ++cc) {
           float v[CW];
-          {
+          if constexpr (SEG) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] = racc[cc * CW + j] * p.wscale_inv;
+          } else {
             float sm[CW];
             const uint32_t col = (uint32_t)((buf * MT + mt) * 2 * NT + cc * CW);
             tmem_ld16x2(tmem_base + lane_addr + col, v, tmem_base + lane_addr + col + NT, sm);
@@ -689,10 +729,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
           if (lane == 0 && key != 0ull) atomicMax(p.head_key + img, key);
         }
-        tc_fence_before();
-        mbar_arrive_cluster(&acc_empty[buf * MT + mt], 0);      // always the leader's barrier
+        if constexpr (!SEG) {
+          tc_fence_before();
+          mbar_arrive_cluster(&acc_empty[buf * MT + mt], 0);      // always the leader's barrier
+        }
       }
-      if (++buf == NBUF) { buf = 0; phc ^= 1u; }
+      if constexpr (!SEG) { if (++buf == NBUF) { buf = 0; phc ^= 1u; } }
     }
   }
 
@@ -705,7 +747,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
-template <int NT, int KS, bool UP, bool WRES = false, bool FIRST = false, int MT_ = 2>
+template <int NT, int KS, bool UP, bool WRES = false, bool FIRST = false, int MT_ = 2, bool SEG = false>
 cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta, const CUtensorMap* w0, const CUtensorMap* w1,
                         int sm_count, cudaStream_t s, double* issued_flops) {
   using Cfg = Tc2Cfg<NT, UP, WRES, MT_>;
@@ -713,7 +755,7 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NT, KS, UP, WRES, FIRST, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NT, KS, UP, WRES, FIRST, MT_, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
@@ -752,6 +794,8 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
   g.out = p.out_layout.plane ? p.out_layout
                              : (p.pool ? h2_standard(p.cout_total, p.hout >> 1, p.wout >> 1) : h2_standard(p.cout_total, p.hout, p.wout));
   g.slices = n_slices;
+  static const bool slice_minor = [] { const char* v = getenv("DCU_SLICE_MINOR"); return !v || atoi(v) != 0; }();
+  g.slice_minor = (slice_minor && n_slices > 1) ? 1 : 0;
   g.pairs_per_slice = (g.tiles_per_slice + 1) / 2;
   g.total_pairs = g.pairs_per_slice * g.slices;
   if (g.total_pairs <= 0) return cudaSuccess;
@@ -773,7 +817,7 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
       return cudaErrorInvalidValue;
     return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, KS, UP, WRES, true>, *ta, *w0, *w1, p, g, *p.host_bn, *p.first_w);
   } else {
-    return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, KS, UP, WRES, false, MT_>, *ta, *w0, *w1, p, g, *p.host_bn, NoFirst());
+    return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, KS, UP, WRES, false, MT_, SEG>, *ta, *w0, *w1, p, g, *p.host_bn, NoFirst());
   }
   return cudaGetLastError();
 }
@@ -781,6 +825,11 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
 }  // namespace
 
 int tc2_block_bytes(int nt) { return 48 * nt; }
+// two-level accumulation (SEG template parameter) is the default; DCU_SEG=0 keeps whole-tile accumulation chains in tensor memory
+bool tc2_segmented() {
+  static const bool seg = [] { const char* v = getenv("DCU_SEG"); return !v || atoi(v) != 0; }();
+  return seg;
+}
 int tc2_flat_rows(int in_row, int pad_or_up, int up) {
   const int back = pad_or_up ? in_row + 1 : 0, fwd = pad_or_up ? in_row + 1 : 2 * in_row + 2;
   return ceil_div(ceil_div(back, 16) * 16 + (up ? 128 : 256) + fwd, 16);
@@ -794,6 +843,14 @@ cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const voi
   const CUtensorMap* w1 = reinterpret_cast<const CUtensorMap*>(tmap_w1);
   const int nt = p.cout_total / n_slices;
   if (p.ksize == 1) return cudaErrorInvalidValue;      // the 1x1 heads stay on the single-CTA kernel
+  const bool seg = tc2_segmented() && nt == 64 && p.first_w == nullptr;
+  if (seg) {
+    if (up) return launch_pair<64, 3, true, false, false, 2, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+    static const bool wres_seg = [] { const char* v = getenv("DCU_WRES"); return !v || atoi(v) != 0; }();
+    if (p.mt1) return launch_pair<64, 3, false, false, false, 1, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+    if (n_slices == 1 && p.cin == 64 && wres_seg) return launch_pair<64, 3, false, true, false, 2, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+    return launch_pair<64, 3, false, false, false, 2, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+  }
   if (up) {
     if (nt == 64) return launch_pair<64, 3, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
     if (nt == 128) return launch_pair<128, 3, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);

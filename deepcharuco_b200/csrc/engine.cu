@@ -1439,10 +1439,10 @@ static int pnp_object_table(DcuEngine* e, int col_count, int row_count, double s
   return DCU_OK;
 }
 
-int dcu_solve_pnp_batch(DcuEngine* e, const int32_t* counts_dev, const int32_t* offsets_dev, const int32_t* kpts_dev,
-                        const float* refined_dev, int n, int col_count, int row_count, double square_len,
-                        const double* camera_matrix9, const double* dist_coeffs, int n_dist, int32_t* ret_dev,
-                        double* rvec_dev, double* tvec_dev, void* stream) {
+static int solve_pnp_batch_rows(DcuEngine* e, const int32_t* counts_dev, const int32_t* offsets_dev, const int32_t* kpts_dev,
+                                const float* refined_dev, int n, int max_rows, int col_count, int row_count, double square_len,
+                                const double* camera_matrix9, const double* dist_coeffs, int n_dist, int32_t* ret_dev,
+                                double* rvec_dev, double* tvec_dev, void* stream) {
   if (!e || !counts_dev || !offsets_dev || !kpts_dev || !camera_matrix9 || !ret_dev || !rvec_dev || !tvec_dev || n < 0 ||
       n_dist < 0 || (n_dist > 0 && !dist_coeffs))
     return fail(DCU_ERR_INVALID, "dcu_solve_pnp_batch: bad argument");
@@ -1452,12 +1452,21 @@ int dcu_solve_pnp_batch(DcuEngine* e, const int32_t* counts_dev, const int32_t* 
   if (rc) return rc;
   PnpParams q{};
   q.counts = counts_dev; q.offsets = offsets_dev; q.kpts = kpts_dev; q.refined = refined_dev;
-  q.obj = e->pnp_obj.as<float>(); q.n = n; q.n_obj = (col_count - 1) * (row_count - 1); q.max_rows = e->cfg.max_patches;
+  q.obj = e->pnp_obj.as<float>(); q.n = n; q.n_obj = (col_count - 1) * (row_count - 1); q.max_rows = max_rows;
   q.ret = ret_dev; q.rvec = rvec_dev; q.tvec = tvec_dev;
   launch_pnp_batch(q, camera_matrix9, dist_coeffs, n_dist, (cudaStream_t)stream);
   if (n > 0) e->launches++;
   CK(cudaGetLastError());
   return DCU_OK;
+}
+
+int dcu_solve_pnp_batch(DcuEngine* e, const int32_t* counts_dev, const int32_t* offsets_dev, const int32_t* kpts_dev,
+                        const float* refined_dev, int n, int col_count, int row_count, double square_len,
+                        const double* camera_matrix9, const double* dist_coeffs, int n_dist, int32_t* ret_dev,
+                        double* rvec_dev, double* tvec_dev, void* stream) {
+  // kpts_dev / refined_dev are the [max_patches] row buffers of dcu_infer_batch: frames whose rows were dropped at capacity are cut there
+  return solve_pnp_batch_rows(e, counts_dev, offsets_dev, kpts_dev, refined_dev, n, e ? e->cfg.max_patches : 0, col_count, row_count,
+                              square_len, camera_matrix9, dist_coeffs, n_dist, ret_dev, rvec_dev, tvec_dev, stream);
 }
 
 int dcu_solve_pnp_batch_host(DcuEngine* e, const int32_t* counts_host, const int32_t* kpts_host, const float* refined_host, int n,
@@ -1484,9 +1493,9 @@ int dcu_solve_pnp_batch_host(DcuEngine* e, const int32_t* counts_host, const int
     PK(r.alloc((size_t)total * 8));
     if (total > 0) PK(cudaMemcpyAsync(r.p, refined_host, (size_t)total * 8, cudaMemcpyHostToDevice, s));
   }
-  int rc = dcu_solve_pnp_batch(e, c.as<int32_t>(), o.as<int32_t>(), k.as<int32_t>(), refined_host ? r.as<float>() : nullptr, n,
-                               col_count, row_count, square_len, camera_matrix9, dist_coeffs, n_dist, ret.as<int32_t>(),
-                               rv.as<double>(), tv.as<double>(), stream);
+  int rc = solve_pnp_batch_rows(e, c.as<int32_t>(), o.as<int32_t>(), k.as<int32_t>(), refined_host ? r.as<float>() : nullptr, n,
+                                (int)std::min<long long>(total, 0x7fffffff), col_count, row_count, square_len, camera_matrix9, dist_coeffs,
+                                n_dist, ret.as<int32_t>(), rv.as<double>(), tv.as<double>(), stream);
   if (rc) { freeall(); return rc; }
   PK(cudaMemcpyAsync(ret_host, ret.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
   PK(cudaMemcpyAsync(rvec_host, rv.p, (size_t)n * 24, cudaMemcpyDeviceToHost, s));
