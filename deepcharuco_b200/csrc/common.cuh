@@ -186,6 +186,14 @@ struct MetricsParams {
   float* l2; float* ratio; int32_t* valid;                      // [n]
 };
 void launch_dc_metrics(const MetricsParams& p, cudaStream_t s);
+// utils.pixel_error (utils.py:33-52) per frame on the engine's result rows and float64 labels (metrics.cu)
+struct PixelErrorParams {
+  const int32_t* counts; const int32_t* offsets; const int32_t* kpts; const float* refined;
+  int n, max_rows;
+  const int32_t* tcounts; const int32_t* toffsets; const double* target;     // labels: [sum tcounts][3] = x, y, id
+  int32_t* status; double* out;                                              // [n], [n][6]
+};
+void launch_pixel_error(const PixelErrorParams& p, cudaStream_t s);
 // per sample |argmax(pred) - argmax(target)|_2 over h x w maps; pred == null: the predicted arg-max comes from pred_corners (col, row)
 void launch_heat_argmax_dist(const float* pred, const int32_t* pred_corners, const float* target, int p, int h, int w, float* dist,
                              cudaStream_t s);

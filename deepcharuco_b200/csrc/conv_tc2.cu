@@ -40,6 +40,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -49,7 +50,7 @@ namespace dcu {
 
 namespace {
 
-constexpr int T2_THREADS = 384;
+constexpr int t2_threads(int cg) { return 128 + 256 * cg; }     // 4 control warps + 8 epilogue warps per channel group
 
 // WRES (weights resident): a 64 -> 64 layer's whole weight set (4 chunks x 3 kernel rows = 12 stages, 110.6 kB per rank) stays in
 // shared memory for the lifetime of the CTA instead of being re-fetched for every tile.  The kernel is bound by the shared-memory
@@ -82,6 +83,8 @@ struct Tc2Geo {
   // sbo = distance between consecutive groups of 8 M rows.  Standard: row_step = sbo = halo_w, a_org = 0.
   int row_step, sbo, a_org;
   int flat, tile_px, lead;     // FLAT: pixels per CTA tile (256; UP: 128), pixels loaded ahead of the tile start (multiple of 16)
+  int seg0;                    // SEG: 16-channel chunks in the FIRST segment of a tile (>= 1); every later chunk is its own segment.  A longer
+                               // first segment widens the window in which the epilogue finishes the previous tile (DCU_SEG_FIRST)
   int slice_minor;             // work items ordered tile-major (item = pair * slices + slice): the slices of one pixel tile run at the same
                                // time on neighbouring clusters, so its halo is read from HBM once and from L2 by the other slices
   H2Layout out;                // output addressing
@@ -299,8 +302,12 @@ struct NoFirst {};
 // epilogue warps drain every finished chunk into fp32 registers with round-to-nearest adds while the next chunk is being issued.
 // Partial sums stay small (shorter chains lose less per step) and the register adds are unbiased.  NT = 64 only (64 running sums per
 // epilogue thread); 128-channel layers run as 64-channel slices in this mode.
-template <int NT, int KS, bool UP, bool WRES, bool FIRST, int MT_ = 2, bool SEG = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+// CG (channel groups, SEG only): the NT channels of an m-tile are shared by CG sets of four epilogue warps (CG = 2: 16 epilogue warps,
+// 32 running sums each).  The accumulator sets are handed back per CHUNK, so the issuer can only run NBUF - 1 chunks ahead of the
+// epilogue: the per-tile tail (BN, ReLU, pooling, fp16 split, stores) has to fit into that window, and with 64 channels per thread it
+// did not (measured: + 35 % on conv1b).  Half the channels per thread halves both the tail and the drains.
+template <int NT, int KS, bool UP, bool WRES, bool FIRST, int MT_ = 2, bool SEG = false, int CG = 1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(t2_threads(CG), 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w0,
                 const __grid_constant__ CUtensorMap tmap_w1, const ConvParams p, const Tc2Geo g, const __grid_constant__ TcBn bn,
                 const __grid_constant__ typename std::conditional<FIRST, FirstWeights, NoFirst>::type fw) {
@@ -309,6 +316,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   using Cfg = Tc2Cfg<NT, UP, WRES, MT_>;
   constexpr int MT = Cfg::MT, NBUF = Cfg::NBUF, B_STAGES = Cfg::B_STAGES;
   static_assert(!SEG || (NT == 64 && !FIRST && NBUF >= 2), "SEG: 64-channel slices, double-buffered accumulators, one m-tile per epilogue group");
+  static_assert(CG == 1 || (SEG && CG == 2), "channel groups exist for the two-level accumulation only");
+  constexpr int NTG = NT / CG;          // channels per epilogue thread
   // UP (input = 2x nearest upsampling of the tensor in HBM): per output phase (a, b) the 3x3 taps collapse to 2x2 taps on
   // the low-resolution tensor, so a weight stage is one of 2 kernel rows = 2 taps x 2 column phases (see header).
   constexpr int ROWS = UP ? 2 : KS, TPR = UP ? 2 : KS, SB = Cfg::STAGE_BLOCKS, TAPS = ROWS * SB;
@@ -341,7 +350,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     for (int i = 0; i < Cfg::A_STAGES; ++i) { mbar_init(&a_full[i], FIRST ? 12 : 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < NBUF; ++i) mbar_init(&acc_full[i], 1);
-    for (int i = 0; i < NBUF * MT; ++i) mbar_init(&acc_empty[i], 256);      // epilogue threads of both CTAs (leader's copy is used)
+    for (int i = 0; i < NBUF * MT; ++i) mbar_init(&acc_empty[i], 256 * CG);      // epilogue threads of both CTAs (leader's copy is used)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -538,7 +547,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         mbar_wait(&a_full[sa], pha);
         tc_fence_after();
         const uint32_t a_hi = a_desc_lo0 + a_base0 + (uint32_t)sa * (Cfg::A_STAGE_BYTES >> 4);
-        if (SEG || q == 0) {          // SEG: a fresh accumulator set per chunk
+        const bool seg_open = !SEG || q == 0 || q >= g.seg0, seg_close = !SEG || q >= g.seg0 - 1;
+        if (SEG ? seg_open : q == 0) {          // SEG: a fresh accumulator set per segment
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) mbar_wait(&acc_empty[buf * MT + mt], phc ^ 1u);
           tc_fence_after();
@@ -563,27 +573,28 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 const uint32_t d = tmem_u + (uint32_t)((buf * MT + mt) * 2 * NT);
                 const uint32_t da_hi = a_row + (uint32_t)kx + (UP ? (uint32_t)mt : mt_off[mt]);
                 const uint32_t da_lo = da_hi + 2u * (uint32_t)halo_px;
-                umma2_f16_w(d, da_hi, a_desc_hi, b_main, b_desc_hi, IDESC_2N, ((SEG ? 0 : q) | ky | kx) ? 1u : 0u);   // [a_hi*w_hi | a_hi*w_lo]
+                umma2_f16_w(d, da_hi, a_desc_hi, b_main, b_desc_hi, IDESC_2N, ((SEG ? (seg_open ? 0 : 1) : q) | ky | kx) ? 1u : 0u);   // [a_hi*w_hi | a_hi*w_lo]
                 umma2_f16_w(d + NT, da_lo, a_desc_hi, b_x, b_desc_hi, IDESC_1N, 1u);                        // + a_lo*w_hi
               }
             }
             if (!WRES) umma2_commit_mc(&b_empty[sb]);
             if (ky == ROWS - 1) umma2_commit_mc(&a_empty[sa]);
-            if (ky == ROWS - 1 && (SEG || q == chunks - 1)) umma2_commit_mc(&acc_full[buf]);
+            if (ky == ROWS - 1 && (SEG ? seg_close : q == chunks - 1)) umma2_commit_mc(&acc_full[buf]);
           }
           __syncwarp();
           if (++sb == B_STAGES) { sb = 0; phb ^= 1u; }
         }
         if (++sa == Cfg::A_STAGES) { sa = 0; pha ^= 1u; }
-        if (SEG) { if (++buf == NBUF) { buf = 0; phc ^= 1u; } }
+        if (SEG && seg_close) { if (++buf == NBUF) { buf = 0; phc ^= 1u; } }
       }
       if (!SEG) { if (++buf == NBUF) { buf = 0; phc ^= 1u; } }
     }
-  } else if (warp >= 4 && (!FIRST || warp < 8) && (!SEG || warp < 4 + 4 * MT)) {
+  } else if (warp >= 4 && (!FIRST || warp < 8) && (!SEG || (((warp - 4) >> 2) & 1) < MT)) {
     // ================= epilogue (both CTAs, each drains its own 128 TMEM lanes) =================
     constexpr int CW = 16;
-    const int grp = (!FIRST && warp >= 8) ? 1 : 0;       // FIRST: warps 4-7 drain both m-tiles (warps 8-11 are the conv1a producers)
-    float racc[SEG ? NT : 1];                            // SEG: this thread's running sums (one pixel x NT channels of m-tile `grp`)
+    const int grp = (!FIRST && ((warp - 4) & 4)) ? 1 : 0;       // m-tile of this warp.  FIRST: warps 4-7 drain both m-tiles (warps 8-11 are the conv1a producers)
+    const int cg = (warp - 4) >> 3;                      // channel group: channels [cg * NTG, (cg + 1) * NTG) of the slice
+    float racc[SEG ? NTG : 1];                           // SEG: this thread's running sums (one pixel x NTG channels of m-tile `grp`)
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;
     const int prow = m >> 3, pcol = m & 7;
@@ -597,15 +608,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       if constexpr (SEG) {
         // drain every finished chunk of m-tile `grp` into registers (RN adds), releasing its accumulator set for the chunk after next
 #pragma unroll
-        for (int j = 0; j < NT; ++j) racc[j] = 0.f;
+        for (int j = 0; j < NTG; ++j) racc[j] = 0.f;
 #pragma unroll 1
-        for (int q = 0; q < chunks; ++q) {
+        for (int q = g.seg0 - 1; q < chunks; ++q) {          // one pass per segment
           mbar_wait<40>(&acc_full[buf], phc);
           tc_fence_after();
 #pragma unroll
-          for (int cc = 0; cc < NT / CW; ++cc) {
+          for (int cc = 0; cc < NTG / CW; ++cc) {
             float v[CW], sm[CW];
-            const uint32_t col = (uint32_t)((buf * MT + grp) * 2 * NT + cc * CW);
+            const uint32_t col = (uint32_t)((buf * MT + grp) * 2 * NT + cg * NTG + cc * CW);
             tmem_ld16x2(tmem_base + lane_addr + col, v, tmem_base + lane_addr + col + NT, sm);
 #pragma unroll
             for (int j = 0; j < CW; ++j) racc[cc * CW + j] += v[j] + sm[j];
@@ -640,8 +651,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           inb = c.valid && (oy < p.hout) && (ox < p.wout);
         }
         float head_sum = 0.f;
-#pragma unroll (SEG ? NT / CW : 1)
-        for (int cc = 0; cc < NT / CW; ++cc) {
+#pragma unroll (SEG ? NTG / CW : 1)
+        for (int cc = 0; cc < NTG / CW; ++cc) {
           float v[CW];
           if constexpr (SEG) {
 #pragma unroll
@@ -653,7 +664,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
             for (int j = 0; j < CW; ++j) v[j] = (v[j] + sm[j]) * p.wscale_inv;
           }
-          const int ch0 = ch_base + cc * CW;
+          const int ch0 = ch_base + cg * NTG + cc * CW;
           if (p.logits != nullptr) {
             if (inb) {
               const size_t plane_o = (size_t)p.hout * p.wout;
@@ -747,7 +758,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
-template <int NT, int KS, bool UP, bool WRES = false, bool FIRST = false, int MT_ = 2, bool SEG = false>
+template <int NT, int KS, bool UP, bool WRES = false, bool FIRST = false, int MT_ = 2, bool SEG = false, int CG = 1>
 cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta, const CUtensorMap* w0, const CUtensorMap* w1,
                         int sm_count, cudaStream_t s, double* issued_flops) {
   using Cfg = Tc2Cfg<NT, UP, WRES, MT_>;
@@ -755,13 +766,14 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NT, KS, UP, WRES, FIRST, MT_, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<NT, KS, UP, WRES, FIRST, MT_, SEG, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   Tc2Geo g{};
   if (UP && (p.pad != 1 || p.pool || p.ups || p.hout != 2 * p.hin || p.wout != 2 * p.win)) return cudaErrorInvalidValue;
   if (MT_ == 1 && (UP || p.flat_in)) return cudaErrorInvalidValue;
+  if (CG != 1 && p.head_w != nullptr) return cudaErrorInvalidValue;      // the fused 1x1 head sums over all channels of a pixel in one thread
   if (p.flat_in) {
     // the batch as one run of pixels; CTA tile = 256 consecutive pixels (UP: 128, the two m-tiles are the column phases)
     if (p.pool || p.ups || p.head_w || p.logits || p.in_period <= 0 || p.in_row <= 0) return cudaErrorInvalidValue;
@@ -794,6 +806,8 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
   g.out = p.out_layout.plane ? p.out_layout
                              : (p.pool ? h2_standard(p.cout_total, p.hout >> 1, p.wout >> 1) : h2_standard(p.cout_total, p.hout, p.wout));
   g.slices = n_slices;
+  static const int seg_first = [] { const char* v = getenv("DCU_SEG_FIRST"); return v ? atoi(v) : 1; }();
+  g.seg0 = std::max(1, std::min(seg_first, p.cin / 16));
   static const bool slice_minor = [] { const char* v = getenv("DCU_SLICE_MINOR"); return !v || atoi(v) != 0; }();
   g.slice_minor = (slice_minor && n_slices > 1) ? 1 : 0;
   g.pairs_per_slice = (g.tiles_per_slice + 1) / 2;
@@ -805,7 +819,7 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
   if (p.host_bn == nullptr) return cudaErrorInvalidValue;
   static const bool pdl = [] { const char* v = getenv("DCU_PDL"); return !v || atoi(v) != 0; }();
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)clusters * 2, 1, 1); cfg.blockDim = dim3(T2_THREADS, 1, 1);
+  cfg.gridDim = dim3((unsigned)clusters * 2, 1, 1); cfg.blockDim = dim3(t2_threads(CG), 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -817,7 +831,7 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
       return cudaErrorInvalidValue;
     return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, KS, UP, WRES, true>, *ta, *w0, *w1, p, g, *p.host_bn, *p.first_w);
   } else {
-    return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, KS, UP, WRES, false, MT_, SEG>, *ta, *w0, *w1, p, g, *p.host_bn, NoFirst());
+    return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<NT, KS, UP, WRES, false, MT_, SEG, CG>, *ta, *w0, *w1, p, g, *p.host_bn, NoFirst());
   }
   return cudaGetLastError();
 }
@@ -826,9 +840,9 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
 
 int tc2_block_bytes(int nt) { return 48 * nt; }
 // two-level accumulation (SEG template parameter) is the default; DCU_SEG=0 keeps whole-tile accumulation chains in tensor memory
-bool tc2_segmented() {
-  static const bool seg = [] { const char* v = getenv("DCU_SEG"); return !v || atoi(v) != 0; }();
-  return seg;
+bool tc2_segmented() {          // read per call: tests switch it between engines of one process
+  const char* v = getenv("DCU_SEG");
+  return !v || atoi(v) != 0;
 }
 int tc2_flat_rows(int in_row, int pad_or_up, int up) {
   const int back = pad_or_up ? in_row + 1 : 0, fwd = pad_or_up ? in_row + 1 : 2 * in_row + 2;
@@ -845,10 +859,18 @@ cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const voi
   if (p.ksize == 1) return cudaErrorInvalidValue;      // the 1x1 heads stay on the single-CTA kernel
   const bool seg = tc2_segmented() && nt == 64 && p.first_w == nullptr;
   if (seg) {
-    if (up) return launch_pair<64, 3, true, false, false, 2, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+    static const int cg = [] { const char* v = getenv("DCU_SEG_CG"); return v ? atoi(v) : 2; }();
     static const bool wres_seg = [] { const char* v = getenv("DCU_WRES"); return !v || atoi(v) != 0; }();
+    const bool wres = n_slices == 1 && p.cin == 64 && wres_seg;
+    if (cg == 2 && p.head_w == nullptr) {
+      if (up) return launch_pair<64, 3, true, false, false, 2, true, 2>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+      if (p.mt1) return launch_pair<64, 3, false, false, false, 1, true, 2>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+      if (wres) return launch_pair<64, 3, false, true, false, 2, true, 2>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+      return launch_pair<64, 3, false, false, false, 2, true, 2>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+    }
+    if (up) return launch_pair<64, 3, true, false, false, 2, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
     if (p.mt1) return launch_pair<64, 3, false, false, false, 1, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
-    if (n_slices == 1 && p.cin == 64 && wres_seg) return launch_pair<64, 3, false, true, false, 2, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+    if (wres) return launch_pair<64, 3, false, true, false, 2, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
     return launch_pair<64, 3, false, false, false, 2, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
   }
   if (up) {

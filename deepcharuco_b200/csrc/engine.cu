@@ -1421,6 +1421,22 @@ int dcu_refinenet_metrics(DcuEngine* e, const float* heat_pred_dev, const int32_
   return DCU_OK;
 }
 
+int dcu_pixel_error(DcuEngine* e, const int32_t* counts_dev, const int32_t* offsets_dev, const int32_t* kpts_dev, const float* refined_dev,
+                    int n, const int32_t* tcounts_dev, const int32_t* toffsets_dev, const double* target_dev, int32_t* status_dev,
+                    double* out_dev, void* stream) {
+  if (!e || !counts_dev || !offsets_dev || !kpts_dev || !refined_dev || !tcounts_dev || !toffsets_dev || !target_dev || !status_dev ||
+      !out_dev || n < 0)
+    return fail(DCU_ERR_INVALID, "dcu_pixel_error: bad argument");
+  CK(cudaSetDevice(e->cfg.device));
+  PixelErrorParams p{};
+  p.counts = counts_dev; p.offsets = offsets_dev; p.kpts = kpts_dev; p.refined = refined_dev; p.n = n; p.max_rows = e->cfg.max_patches;
+  p.tcounts = tcounts_dev; p.toffsets = toffsets_dev; p.target = target_dev; p.status = status_dev; p.out = out_dev;
+  launch_pixel_error(p, (cudaStream_t)stream);
+  if (n > 0) e->launches++;
+  CK(cudaGetLastError());
+  return DCU_OK;
+}
+
 // ---- batched solve_pnp (inference.py:15-29) ----
 static int pnp_object_table(DcuEngine* e, int col_count, int row_count, double square_len) {
   // object_points[:, :2] = meshgrid(arange(1,row_count), arange(1,col_count)).reshape(2,-1).T * square_len  (float32 storage):

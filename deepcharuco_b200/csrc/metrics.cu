@@ -116,7 +116,115 @@ heat_argmax_dist_kernel(const float* __restrict__ pred, const int32_t* __restric
   }
 }
 
+// ---- utils.pixel_error (/root/reference/src/utils.py:33-52), batched -----------------------------------------------------------
+// Per frame: raw corners (x, y, id: the engine's integer pixels), refined corners (x, y), labels (x, y, id as float64), and
+//   d         = compute_l2_distance(raw, labels)      d_ref = compute_l2_distance(refined, labels)      d_rr = compute_l2_distance(refined, raw)
+// with compute_l2_distance (utils.py:6-30): distances = zeros(len(target_ids)); for i, id in enumerate(unique(target_ids)): the largest
+// float64 distance between the predictions with that id and the target(s) with that id (numpy broadcasting of (m,2) - (t,2): needs
+// m == t, m == 1 or t == 1 -- anything else raises in the reference and is reported as status -1 here); ids nobody predicted keep 0.
+// out[f] = {mean d, mean d_ref, mean d_rr, max d, max d_ref, max d_rr}.  status[f]: 1 evaluated; 0 skipped like the caller / the
+// function do (no labels, no predictions, or a predicted id that is not among the labels: utils.py:34-35); -1 shapes numpy rejects.
+// All float64 with separately rounded multiplies / adds (numpy has no FMA contraction) and numpy's pairwise summation order, so the
+// numbers are bit-identical with the reference's.  One thread per frame: a frame has a few dozen corners.
+constexpr int PE_MAX_IDS = 64;
+constexpr int PE_MAX_ROWS = 256;
+
+__device__ double np_pairwise_sum(const double* a, int n) {          // numpy's DOUBLE_pairwise_sum for n <= 128 (one block)
+  if (n < 8) {
+    double r = 0.0;
+    for (int i = 0; i < n; ++i) r = __dadd_rn(r, a[i]);
+    return r;
+  }
+  double r[8];
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+  return res;
+}
+
+struct PeSet { const double* x; const double* y; const int* id; int n; };    // a list of (x, y, id) rows in local memory
+
+// distances[] (length tgt.n) as utils.compute_l2_distance; returns false on a broadcast numpy would reject
+__device__ bool pe_l2(const PeSet& pred, const PeSet& tgt, double* distances) {
+  for (int i = 0; i < tgt.n; ++i) distances[i] = 0.0;
+  int slot = 0;
+  for (int idv = 0; idv < PE_MAX_IDS; ++idv) {                      // ascending id = np.unique order
+    int t = 0, m = 0;
+    for (int j = 0; j < tgt.n; ++j) t += tgt.id[j] == idv;
+    if (t == 0) continue;
+    for (int j = 0; j < pred.n; ++j) m += pred.id[j] == idv;
+    const int i = slot++;
+    if (m == 0) continue;
+    if (!(m == t || m == 1 || t == 1)) return false;
+    const int pairs = m > t ? m : t;
+    double mx = 0.0;
+    int jp = -1, jt = -1;
+    for (int k = 0; k < pairs; ++k) {
+      if (k == 0 || m > 1) { do { ++jp; } while (pred.id[jp] != idv); }
+      if (k == 0 || t > 1) { do { ++jt; } while (tgt.id[jt] != idv); }
+      const double dx = __dsub_rn(pred.x[jp], tgt.x[jt]), dy = __dsub_rn(pred.y[jp], tgt.y[jt]);
+      const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+      if (k == 0 || d > mx) mx = d;
+    }
+    distances[i] = mx;
+  }
+  return true;
+}
+
+__global__ void pixel_error_kernel(PixelErrorParams p) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= p.n) return;
+  double* out = p.out + 6 * (size_t)f;
+  for (int k = 0; k < 6; ++k) out[k] = 0.0;
+  const int off = p.offsets[f];
+  const int K = max(0, min(p.counts[f], p.max_rows - off));
+  const int T = p.tcounts[f];
+  if (K == 0 || T == 0) { p.status[f] = 0; return; }               // `if len(label_kpts) != 0 and len(keypoints) != 0` (inference.py:154)
+  if (K > PE_MAX_ROWS || T > PE_MAX_ROWS) { p.status[f] = -1; return; }
+  double rx[PE_MAX_ROWS], ry[PE_MAX_ROWS], fx[PE_MAX_ROWS], fy[PE_MAX_ROWS], tx[PE_MAX_ROWS], ty[PE_MAX_ROWS], dist[PE_MAX_ROWS];
+  int rid[PE_MAX_ROWS], tid[PE_MAX_ROWS];
+  const double* tg = p.target + 3 * (size_t)p.toffsets[f];
+  bool ok = true;
+  for (int j = 0; j < T; ++j) {
+    tx[j] = tg[3 * j]; ty[j] = tg[3 * j + 1];
+    const double idd = tg[3 * j + 2];
+    tid[j] = (int)idd;
+    ok = ok && idd >= 0.0 && idd < (double)PE_MAX_IDS && (double)tid[j] == idd;
+  }
+  for (int j = 0; j < K; ++j) {
+    const int4 r = reinterpret_cast<const int4*>(p.kpts)[off + j];
+    rx[j] = (double)r.x; ry[j] = (double)r.y; rid[j] = r.z;
+    fx[j] = (double)p.refined[2 * (size_t)(off + j)]; fy[j] = (double)p.refined[2 * (size_t)(off + j) + 1];
+    ok = ok && r.z >= 0 && r.z < PE_MAX_IDS;
+  }
+  if (!ok) { p.status[f] = -1; return; }
+  for (int j = 0; j < K; ++j) {                                    // set(raw ids).issubset(set(label ids)), utils.py:34
+    bool found = false;
+    for (int i = 0; i < T; ++i) found = found || tid[i] == rid[j];
+    if (!found) { p.status[f] = 0; return; }
+  }
+  const PeSet raw{rx, ry, rid, K}, ref{fx, fy, rid, K}, lab{tx, ty, tid, T};
+  struct { const PeSet* a; const PeSet* b; } legs[3] = {{&raw, &lab}, {&ref, &lab}, {&ref, &raw}};
+  for (int leg = 0; leg < 3; ++leg) {
+    if (!pe_l2(*legs[leg].a, *legs[leg].b, dist)) { p.status[f] = -1; return; }
+    const int n = legs[leg].b->n;
+    double mx = dist[0];
+    for (int i = 1; i < n; ++i) mx = dist[i] > mx ? dist[i] : mx;
+    out[leg] = __ddiv_rn(np_pairwise_sum(dist, n), (double)n);      // ndarray.mean(): pairwise add.reduce / n
+    out[3 + leg] = mx;
+  }
+  p.status[f] = 1;
+}
+
 }  // namespace
+
+void launch_pixel_error(const PixelErrorParams& p, cudaStream_t s) {
+  if (p.n <= 0) return;
+  pixel_error_kernel<<<(p.n + 31) / 32, 32, 0, s>>>(p);
+}
 
 void launch_heat_argmax_dist(const float* pred, const int32_t* pred_corners, const float* target, int p, int h, int w, float* dist,
                              cudaStream_t s) {

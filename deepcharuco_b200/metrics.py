@@ -140,3 +140,69 @@ class Refinenet_Metrics:
 
     def compute(self):
         return self.distance
+
+
+def _pack_targets(target_list):
+    tc = np.array([0 if np.asarray(t).size == 0 else np.asarray(t).shape[0] for t in target_list], np.int32)
+    rows = [np.asarray(t, np.float64).reshape(-1, 3) for t in target_list if np.asarray(t).size]
+    flat = np.ascontiguousarray(np.concatenate(rows, 0) if rows else np.zeros((0, 3), np.float64))
+    toff = np.concatenate([[0], np.cumsum(tc)[:-1]]).astype(np.int32) if len(tc) else np.zeros(0, np.int32)
+    return tc, toff, flat
+
+
+def pixel_error_batch(raw_list, refined_list, target_list, device=0):
+    """`utils.pixel_error` (/root/reference/src/utils.py:33-52) for every frame of a batch in ONE kernel launch (`dcu_pixel_error`).
+
+    raw_list / refined_list: what `infer_batch(..., None)` / `infer_batch(..., refinenet)` return (per frame (K,3) [x, y, id] or an
+    empty array); target_list: per frame the label keypoints (T,3) [x, y, id] (float).  Returns (status int32 [N], out float64 [N,6]):
+    out[f] = (mean raw, mean refined, mean refined-vs-raw, max raw, max refined, max refined-vs-raw) error in pixels, bit-identical
+    with the reference's float64 numbers; status 1 = evaluated, 0 = skipped like the reference ((None, None) or no labels / corners),
+    -1 = a frame the reference's numpy code would raise on."""
+    import torch
+    from .inference import _scratch_context
+    n = len(raw_list)
+    assert len(refined_list) == n and len(target_list) == n
+    if n == 0:
+        return np.zeros(0, np.int32), np.zeros((0, 6), np.float64)
+    counts = np.array([0 if np.asarray(r).size == 0 else np.asarray(r).shape[0] for r in raw_list], np.int32)
+    for r, f in zip(raw_list, refined_list):
+        assert (np.asarray(r).size == 0) == (np.asarray(f).size == 0) and (np.asarray(r).size == 0 or np.asarray(r).shape == np.asarray(f).shape)
+    total = int(counts.sum())
+    offsets = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int32)
+    kpts = np.zeros((max(total, 1), 4), np.int32)
+    refined = np.zeros((max(total, 1), 2), np.float32)
+    if total:
+        raw = np.concatenate([np.asarray(r).reshape(-1, 3) for r in raw_list if np.asarray(r).size], 0)
+        ref = np.concatenate([np.asarray(r).reshape(-1, 3) for r in refined_list if np.asarray(r).size], 0)
+        assert np.array_equal(raw[:, 2].astype(np.int64), ref[:, 2].astype(np.int64)), "raw and refined rows must list the same ids"
+        kpts[:total, :3] = raw.astype(np.int64)
+        refined[:total] = ref[:, :2]
+    tc, toff, tflat = _pack_targets(target_list)
+    eng = _scratch_context(16, int(device)).engine(240, 320, max_batch=1, max_patches=max(256, total))
+    dev = torch.device("cuda", eng.device)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_counts, d_offsets, d_kpts, d_ref, d_tc, d_toff = d(counts), d(offsets), d(kpts), d(refined), d(tc), d(toff)
+    d_t = d(tflat if tflat.size else np.zeros((1, 3)))
+    status = torch.empty(n, dtype=torch.int32, device=dev)
+    out = torch.empty((n, 6), dtype=torch.float64, device=dev)
+    N.check(N.lib().dcu_pixel_error(eng.handle, d_counts.data_ptr(), d_offsets.data_ptr(), d_kpts.data_ptr(), d_ref.data_ptr(), n,
+                                    d_tc.data_ptr(), d_toff.data_ptr(), d_t.data_ptr(), status.data_ptr(), out.data_ptr(),
+                                    torch.cuda.current_stream(dev).cuda_stream))
+    return status.cpu().numpy(), out.cpu().numpy()
+
+
+def pixel_error(kpts_raw, kpts_ref, kpts_target, verbose=True, device=0):
+    """Drop-in for `utils.pixel_error(kpts_raw, kpts_ref, kpts_target)` (utils.py:33-52): returns (mean raw error, mean refined
+    error) in pixels, or (None, None) when a predicted id has no label; prints the reference's summary lines when `verbose`."""
+    status, out = pixel_error_batch([kpts_raw], [kpts_ref], [kpts_target], device=device)
+    if status[0] < 0:
+        raise ValueError("operands could not be broadcast together (several predictions and several labels of one id)")
+    if status[0] == 0:
+        return None, None
+    if verbose:
+        found = np.unique(np.asarray(kpts_raw)[:, 2])
+        print(f'Errors in pixels of the {len(found)}/{len(np.asarray(kpts_target)[:, 2])} kpts found:')
+        print(f'Mean error raw: {out[0, 0]:<5.3f} Max error raw: {out[0, 3]:<5.3f}')
+        print(f'Mean error ref: {out[0, 1]:<5.3f} Max error ref: {out[0, 4]:<5.3f}')
+        print(f'Mean dist raw/ref: {out[0, 2]:<5.3f} Max dist raw/ref: {out[0, 5]:<5.3f}')
+    return out[0, 0], out[0, 1]

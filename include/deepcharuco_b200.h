@@ -193,6 +193,18 @@ int dcu_dc_metrics(DcuEngine* e, const int32_t* counts_dev, const int32_t* offse
                    const int64_t* loc_target_dev, const int64_t* ids_target_dev, int dust_bin_ids, float* l2_dev,
                    float* ratio_dev, int32_t* valid_dev, void* stream);
 
+/* The reference's pixel-error evaluation (utils.pixel_error, /root/reference/src/utils.py:33-52, used by the up_scale = 8 loop of
+ * inference.py:110-171) for every frame of a batch, on the device-resident rows of dcu_infer_batch (kpts_dev {x, y, id, cell},
+ * refined_dev {x, y}) against float64 labels target_dev [sum tcounts][3] = {x, y, id}, frame f owning rows
+ * [toffsets_dev[f], +tcounts_dev[f]).  out_dev [n][6] = {mean, mean_refined, mean_refined_vs_raw, max, max_refined, max_refined_vs_raw}
+ * of compute_l2_distance (utils.py:6-30; float64, bit-identical with numpy incl. its summation order).  status_dev[f] = 1 evaluated;
+ * 0 skipped as the reference skips it (no labels / no corners / a predicted id that has no label: returns (None, None)); -1 where
+ * numpy's broadcasting would raise (several predictions AND several labels of one id in different numbers), ids outside [0, 64)
+ * or more than 256 rows in a frame. */
+int dcu_pixel_error(DcuEngine* e, const int32_t* counts_dev, const int32_t* offsets_dev, const int32_t* kpts_dev, const float* refined_dev,
+                    int n, const int32_t* tcounts_dev, const int32_t* toffsets_dev, const double* target_dev, int32_t* status_dev,
+                    double* out_dev, void* stream);
+
 /* RefineNet validation metric on the device: the per-sample part of Refinenet_Metrics.update (models/metrics.py:141-158):
  * dist[i] = L2 distance in heat-map pixels between the arg-max of the predicted 64x64 heat map and the arg-max of the target map
  * (first maximum of the flattened map).  The prediction is either a heat map tensor heat_pred_dev [p][64][64] or, when that is

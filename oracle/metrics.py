@@ -101,3 +101,32 @@ class RefinenetMetrics:
 
     def compute(self):
         return self.distance
+
+
+def utils_l2_distance(keypoints, ids, target_keypoints, target_ids):
+    """/root/reference/src/utils.py:6-30 -- distances = zeros(len(target_ids)); for i, id in enumerate(unique(target_ids)): the
+    largest float64 distance between the keypoints with that id and the target(s) with that id (numpy broadcasting, raises like
+    the reference on (m,2) - (t,2) with m != t, m != 1, t != 1); ids nobody predicted keep 0.  None without targets."""
+    distances = np.zeros((len(target_ids),))
+    if distances.size == 0:
+        return None
+    for i, idv in enumerate(np.unique(target_ids)):
+        mask = np.nonzero(ids == idv)[0]
+        tmask = np.nonzero(target_ids == idv)[0]
+        if mask.size == 0 or tmask.size == 0:
+            continue
+        diff = keypoints[mask] - target_keypoints[tmask]
+        dist = np.sqrt((diff * diff).sum(axis=1))            # np.linalg.norm(ord=2, axis=1) on real input
+        distances[i] = np.max(dist)
+    return distances
+
+
+def pixel_error(kpts_raw, kpts_ref, kpts_target):
+    """utils.py:33-52 without the prints -> (status, [mean d, mean d_ref, mean d_raw_ref, max d, max d_ref, max d_raw_ref]);
+    status 0 = the reference returns (None, None) (a raw id without a label)."""
+    if not set(kpts_raw[:, 2]).issubset(set(kpts_target[:, 2])):
+        return 0, None
+    d = utils_l2_distance(kpts_raw[:, :2], kpts_raw[:, 2], kpts_target[:, :2], kpts_target[:, 2])
+    d_ref = utils_l2_distance(kpts_ref[:, :2], kpts_ref[:, 2], kpts_target[:, :2], kpts_target[:, 2])
+    d_rr = utils_l2_distance(kpts_ref[:, :2], kpts_ref[:, 2], kpts_raw[:, :2], kpts_raw[:, 2])
+    return 1, np.array([d.mean(), d_ref.mean(), d_rr.mean(), d.max(), d_ref.max(), d_rr.max()])

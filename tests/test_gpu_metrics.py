@@ -123,3 +123,41 @@ def test_capacity_is_an_error_not_an_overrun(states):
             e.infer_batch_host(frames, 16, True)
     finally:
         e.close()
+
+
+def test_pixel_error_batch_is_bit_identical_with_the_reference(models):
+    """utils.pixel_error (utils.py:33-52) for a whole batch in one launch: float64 means / maxima bit-identical with the numbers the
+    unmodified reference produced (tests/golden/pixel_error_seed0.npz), same skip rules; single-frame drop-in returns the same pair."""
+    from test_oracle_metrics import pixel_error_case
+    from deepcharuco_b200.metrics import pixel_error, pixel_error_batch
+    raws, refs, targets, p = pixel_error_case()
+    status, out = pixel_error_batch(raws, refs, targets)
+    assert np.array_equal(status, p["status"].astype(np.int32))
+    ok = status == 1
+    assert ok.sum() >= 10 and np.array_equal(out[ok], p["out"][ok])
+    i = int(np.nonzero(ok)[0][0])
+    a, b = pixel_error(raws[i], refs[i], targets[i], verbose=False)
+    assert (a, b) == (p["out"][i, 0], p["out"][i, 1])
+    j = int(np.nonzero(p["status"] == 0)[0][0])
+    assert pixel_error(raws[j], refs[j], targets[j], verbose=False) == (None, None) or raws[j].shape[0] == 0
+    # several predictions AND several labels of one id in different numbers: numpy raises in the reference
+    raw = np.array([[10, 10, 1], [20, 20, 1], [30, 30, 1]], np.int64)
+    tgt = np.array([[10.0, 10.0, 1.0], [21.0, 20.0, 1.0]])
+    st, _ = pixel_error_batch([raw], [raw.astype(np.float64)], [tgt])
+    assert st[0] == -1
+
+
+def test_pixel_error_on_engine_results(models, golden_synth):
+    """End to end: frames -> engine (raw + refined) -> pixel error against labels = the reference's own refined corners: the
+    refined error is 0 wherever the engine's arg-max equals the reference's, the raw error is the sub-pixel offset (< 0.75 px)."""
+    from deepcharuco_b200.metrics import pixel_error_batch
+    deepc, refinenet = models
+    g = golden_synth
+    from conftest import split_rows
+    refined = dc.infer_batch(g["frames"], 16, deepc, refinenet)
+    raw = dc.infer_batch(g["frames"], 16, deepc, None)
+    labels = split_rows(g["out_refined"], g["counts"])
+    status, out = pixel_error_batch(raw, refined, labels)
+    assert (status == 1).all()
+    assert out[:, 1].max() <= 1e-3 and 0.2 < out[:, 0].mean() < 0.75
+    assert np.array_equal(out[:, 0], out[:, 2])          # refined == label, so raw-vs-label == refined-vs-raw (symmetric distances)

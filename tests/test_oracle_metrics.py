@@ -42,3 +42,29 @@ def test_refinenet_metrics_oracle_matches_reference():
     assert np.allclose(m.compute(), r["after_update1"], rtol=1e-6)
     m.update(heat[5:20, None], target[5:20])
     assert np.allclose(m.compute(), r["after_update2"], rtol=1e-6)
+
+
+def pixel_error_case():
+    """(raw, refined, target) per frame + the reference's status / numbers (tests/golden/pixel_error_seed0.npz, made by
+    tools/make_golden_pixel_error.py from the unmodified reference's utils.pixel_error)."""
+    from conftest import split_rows
+    raws, refs = [], []
+    for name in ("synthetic_320x240_seed0.npz", "edge_cases.npz"):
+        g = load_golden(name)
+        raws += split_rows(g["out_raw"], g["counts"]); refs += split_rows(g["out_refined"], g["counts"])
+    p = load_golden("pixel_error_seed0.npz")
+    targets = split_rows(p["targets"], p["target_counts"])
+    return raws, refs, targets, p
+
+
+def test_pixel_error_oracle_matches_reference():
+    raws, refs, targets, p = pixel_error_case()
+    assert len(raws) == len(targets) == len(p["status"]) and p["status"].sum() >= 10
+    for raw, ref, t, st, out in zip(raws, refs, targets, p["status"], p["out"]):
+        if raw.shape[0] == 0 or t.shape[0] == 0:
+            assert st == 0
+            continue
+        got_st, got = oracle.metrics.pixel_error(raw, ref, t)
+        assert got_st == st
+        if st:
+            assert np.array_equal(got, out)            # float64, bit-identical with the reference
