@@ -20,7 +20,7 @@ CONV_DEFAULT = CONV_TCGEN05   # tcgen05 tensor-core path (fp16 hi/lo split); CON
 EXPORTS = [
     "dcu_create", "dcu_destroy", "dcu_detector_forward", "dcu_detector_forward_f32", "dcu_extract_patches",
     "dcu_decode_gather", "dcu_refine_forward", "dcu_infer_batch", "dcu_infer_batch_host", "dcu_infer_batch_host_bgr", "dcu_bgr_to_gray",
-    "dcu_debug_conv_layer", "dcu_debug_tc_stats", "dcu_set_conv_impl", "dcu_launch_count", "dcu_profile_enable", "dcu_profile_read", "dcu_profile_read_issued", "dcu_solve_pnp_batch", "dcu_solve_pnp_batch_host", "dcu_dc_metrics", "dcu_refinenet_metrics", "dcu_pixel_error", "dcu_profile_records", "dcu_detector_flops_per_frame",
+    "dcu_debug_conv_layer", "dcu_debug_tc_stats", "dcu_set_conv_impl", "dcu_launch_count", "dcu_profile_enable", "dcu_profile_read", "dcu_profile_read_issued", "dcu_solve_pnp_batch", "dcu_solve_pnp_batch_host", "dcu_dc_metrics", "dcu_refinenet_metrics", "dcu_pixel_error", "dcu_synth_frames", "dcu_warp_perspective_u8", "dcu_profile_records", "dcu_detector_flops_per_frame",
     "dcu_refine_flops_per_patch", "dcu_last_error", "dcu_version",
 ]
 
@@ -28,6 +28,12 @@ EXPORTS = [
 class DcuConvLayer(C.Structure):
     _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p), ("alpha", C.c_void_p), ("beta", C.c_void_p),
                 ("cin", C.c_int32), ("cout", C.c_int32), ("ksize", C.c_int32)]
+
+
+class DcuSynthFrame(C.Structure):
+    _fields_ = [("lat_step", C.c_int32), ("lat_h", C.c_int32), ("lat_w", C.c_int32), ("n_boards", C.c_int32),
+                ("bg_lo", C.c_float), ("bg_hi", C.c_float), ("gain", C.c_float), ("reserved", C.c_float),
+                ("blur_w", C.c_float * 16), ("hinv", (C.c_double * 9) * 4)]
 
 
 class DcuConfig(C.Structure):
@@ -77,6 +83,8 @@ def lib():
     L.dcu_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     L.dcu_profile_read_issued.argtypes = [vp, i32, C.POINTER(C.c_double)]
     L.dcu_refinenet_metrics.argtypes = [vp, vp, vp, vp, i32, vp, vp]
+    L.dcu_synth_frames.argtypes = [vp, vp, i32, C.c_uint64, i32, vp, i32, vp, vp]
+    L.dcu_warp_perspective_u8.argtypes = [vp, vp, i32, i32, vp, vp, i32, i32, vp]
     L.dcu_pixel_error.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     L.dcu_dc_metrics.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp]
     L.dcu_solve_pnp_batch.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, C.c_double, vp, vp, i32, vp, vp, vp, vp]

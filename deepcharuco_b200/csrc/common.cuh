@@ -159,7 +159,7 @@ cudaError_t launch_conv3x3_tc(const ConvParams& p, const float* w_blocks, int n_
 
 // CTA-pair (cta_group::2) variant, conv_tc2.cu
 int tc2_block_bytes(int nt);
-bool tc2_segmented();          // two-level accumulation on (default; DCU_SEG=0: off) -> every layer runs in 64-channel slices
+bool tc2_segmented(int cin);   // two-level accumulation for a layer with cin input channels (DCU_SEG policy) -> it runs in 64-channel slices
 int tc2_stage_blocks(int up);       // weight blocks per bulk-copy stage (tensor-map box)
 // up != 0: p.in is the LOW-resolution tensor (hin x win) whose 2x nearest upsampling is the layer's input; hout = 2*hin
 int tc2_flat_rows(int in_row, int pad_or_up, int up);   // FLAT mode: rows of 16 pixels per halo box (tensor-map box height)
@@ -197,6 +197,14 @@ void launch_pixel_error(const PixelErrorParams& p, cudaStream_t s);
 // per sample |argmax(pred) - argmax(target)|_2 over h x w maps; pred == null: the predicted arg-max comes from pred_corners (col, row)
 void launch_heat_argmax_dist(const float* pred, const int32_t* pred_corners, const float* target, int p, int h, int w, float* dist,
                              cudaStream_t s);
+
+// synthetic frames (synth.cu); DcuSynthFrame is declared in include/deepcharuco_b200.h
+}  // namespace dcu
+struct DcuSynthFrame;
+namespace dcu {
+cudaError_t launch_synth_frames(const ::DcuSynthFrame* params_dev, const uint8_t* board_dev, int board_px, uint8_t* lattice_dev, int lat_cap,
+                                uint64_t seed, int first_index, int n, int H, int W, uint8_t* frames_dev, cudaStream_t s);
+cudaError_t launch_warp_perspective_u8(const uint8_t* src, int sh, int sw, const double* minv_dev, uint8_t* dst, int H, int W, cudaStream_t s);
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

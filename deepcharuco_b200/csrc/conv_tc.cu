@@ -540,7 +540,7 @@ int tc_supported_shape(int cin, int cout) {
   // NT = 128 accumulator set costs more than reading the activations twice with double-buffered NT = 64 slices (DCU_NT64=0: off)
   static const int nt64 = [] { const char* v = getenv("DCU_NT64"); return v ? atoi(v) : 1; }();
   if (nt64 >= 1 && cin == 64 && cout == 128) return 64;
-  if ((nt64 >= 2 || tc2_segmented()) && cout % 64 == 0 && cout <= 512) return 64;      // two-level accumulation keeps 64 running sums per epilogue thread
+  if ((nt64 >= 2 || tc2_segmented(cin)) && cout % 64 == 0 && cout <= 512) return 64;      // two-level accumulation keeps 64 running sums per epilogue thread
   if (cout % 128 == 0 && cout <= 512) return 128;
   return 0;
 }

@@ -83,8 +83,8 @@ struct Tc2Geo {
   // sbo = distance between consecutive groups of 8 M rows.  Standard: row_step = sbo = halo_w, a_org = 0.
   int row_step, sbo, a_org;
   int flat, tile_px, lead;     // FLAT: pixels per CTA tile (256; UP: 128), pixels loaded ahead of the tile start (multiple of 16)
-  int seg0;                    // SEG: 16-channel chunks in the FIRST segment of a tile (>= 1); every later chunk is its own segment.  A longer
-                               // first segment widens the window in which the epilogue finishes the previous tile (DCU_SEG_FIRST)
+  int seg0, segc;              // SEG: 16-channel chunks in the FIRST segment of a tile and in every later segment (>= 1).  Each drain costs
+                               // 128 TMEM columns x 128 lanes of tcgen05.ld per m-tile (64 B / cycle / SM): 4-chunk layers afford 2 segments
   int slice_minor;             // work items ordered tile-major (item = pair * slices + slice): the slices of one pixel tile run at the same
                                // time on neighbouring clusters, so its halo is read from HBM once and from L2 by the other slices
   H2Layout out;                // output addressing
@@ -547,7 +547,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         mbar_wait(&a_full[sa], pha);
         tc_fence_after();
         const uint32_t a_hi = a_desc_lo0 + a_base0 + (uint32_t)sa * (Cfg::A_STAGE_BYTES >> 4);
-        const bool seg_open = !SEG || q == 0 || q >= g.seg0, seg_close = !SEG || q >= g.seg0 - 1;
+        const bool seg_open = !SEG || q == 0 || (q >= g.seg0 && (q - g.seg0) % g.segc == 0);
+        const bool seg_close = !SEG || q == chunks - 1 || (q >= g.seg0 - 1 && (q - g.seg0 + 1) % g.segc == 0);
         if (SEG ? seg_open : q == 0) {          // SEG: a fresh accumulator set per segment
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) mbar_wait(&acc_empty[buf * MT + mt], phc ^ 1u);
@@ -610,7 +611,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
         for (int j = 0; j < NTG; ++j) racc[j] = 0.f;
 #pragma unroll 1
-        for (int q = g.seg0 - 1; q < chunks; ++q) {          // one pass per segment
+        for (int q = 0; q < chunks; ++q) {          // one pass per segment
+          if (!(q == chunks - 1 || (q >= g.seg0 - 1 && (q - g.seg0 + 1) % g.segc == 0))) continue;
           mbar_wait<40>(&acc_full[buf], phc);
           tc_fence_after();
 #pragma unroll
@@ -806,8 +808,13 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
   g.out = p.out_layout.plane ? p.out_layout
                              : (p.pool ? h2_standard(p.cout_total, p.hout >> 1, p.wout >> 1) : h2_standard(p.cout_total, p.hout, p.wout));
   g.slices = n_slices;
-  static const int seg_first = [] { const char* v = getenv("DCU_SEG_FIRST"); return v ? atoi(v) : 1; }();
-  g.seg0 = std::max(1, std::min(seg_first, p.cin / 16));
+  // chunks per segment: layers with 4 chunks (64 input channels) have ~8k-cycle tiles and afford two drains of 2k cycles each;
+  // 8-chunk layers drain every chunk
+  static const int seg_c64 = [] { const char* v = getenv("DCU_SEG_CHUNKS64"); return v ? atoi(v) : 2; }();
+  static const int seg_c128 = [] { const char* v = getenv("DCU_SEG_CHUNKS128"); return v ? atoi(v) : 1; }();
+  static const int seg_first = [] { const char* v = getenv("DCU_SEG_FIRST"); return v ? atoi(v) : 0; }();
+  g.segc = std::max(1, std::min(p.cin <= 64 ? seg_c64 : seg_c128, p.cin / 16));
+  g.seg0 = std::max(1, std::min(seg_first > 0 ? seg_first : g.segc, p.cin / 16));
   static const bool slice_minor = [] { const char* v = getenv("DCU_SLICE_MINOR"); return !v || atoi(v) != 0; }();
   g.slice_minor = (slice_minor && n_slices > 1) ? 1 : 0;
   g.pairs_per_slice = (g.tiles_per_slice + 1) / 2;
@@ -840,9 +847,16 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
 
 int tc2_block_bytes(int nt) { return 48 * nt; }
 // two-level accumulation (SEG template parameter) is the default; DCU_SEG=0 keeps whole-tile accumulation chains in tensor memory
-bool tc2_segmented() {          // read per call: tests switch it between engines of one process
+// DCU_SEG: 0 = whole-tile accumulation chains in tensor memory everywhere, 1 = two-level accumulation on every layer,
+// 2 = on the layers with >= 128 input channels only (chains of 72 MMAs; their tiles are long enough to hide the extra drains).
+// Read per call: tests switch it between engines of one process.
+int tc2_seg_policy() {
   const char* v = getenv("DCU_SEG");
-  return !v || atoi(v) != 0;
+  return v ? atoi(v) : 1;
+}
+bool tc2_segmented(int cin) {
+  const int pol = tc2_seg_policy();
+  return pol == 1 || (pol == 2 && cin >= 128);
 }
 int tc2_flat_rows(int in_row, int pad_or_up, int up) {
   const int back = pad_or_up ? in_row + 1 : 0, fwd = pad_or_up ? in_row + 1 : 2 * in_row + 2;
@@ -857,7 +871,7 @@ cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const voi
   const CUtensorMap* w1 = reinterpret_cast<const CUtensorMap*>(tmap_w1);
   const int nt = p.cout_total / n_slices;
   if (p.ksize == 1) return cudaErrorInvalidValue;      // the 1x1 heads stay on the single-CTA kernel
-  const bool seg = tc2_segmented() && nt == 64 && p.first_w == nullptr;
+  const bool seg = tc2_segmented(p.cin) && nt == 64 && p.first_w == nullptr;
   if (seg) {
     static const int cg = [] { const char* v = getenv("DCU_SEG_CG"); return v ? atoi(v) : 2; }();
     static const bool wres_seg = [] { const char* v = getenv("DCU_WRES"); return !v || atoi(v) != 0; }();

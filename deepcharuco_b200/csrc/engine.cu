@@ -330,6 +330,7 @@ struct DcuEngine {
   bool arg_heads = true;        // DCU_ARG_HEADS=0: heads write fp32 logits and the decode re-reads all 82 planes
   bool arg_heads_now = false;   // set around the fused pipeline's detector + decode
   DevBuf counts, offsets, total, kpts, patches, keys, refined, scan_state, frames;
+  DevBuf synth_params, synth_lat, synth_m;   // dcu_synth_frames / dcu_warp_perspective_u8 scratch (grown on demand)
   DevBuf pnp_obj;               // [n_obj][2] board corner table of the last solve_pnp geometry
   int pnp_cols = 0, pnp_rows = 0; double pnp_sq = 0.0;
   DevBuf bgr;                   // [max_batch][H][W][3] staging for the BGR entry point (allocated on first use)
@@ -377,7 +378,7 @@ struct DcuEngine {
     if (gstream) cudaStreamDestroy(gstream);
     if (ev_start) cudaEventDestroy(ev_start);
     for (int i = 0; i < 2; ++i) { if (ev_done[i]) cudaEventDestroy(ev_done[i]); if (ev_free[i]) cudaEventDestroy(ev_free[i]); }
-    DevBuf* all[] = {&loc_arg, &ids_arg, &pnp_obj, &flat8[0], &flat8[1], &flat8[2], &bgr, &c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
+    DevBuf* all[] = {&synth_params, &synth_lat, &synth_m, &loc_arg, &ids_arg, &pnp_obj, &flat8[0], &flat8[1], &flat8[2], &bgr, &c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
                      &ids, &counts, &offsets, &total, &kpts, &patches, &keys, &refined, &scan_state, &frames};
     for (DevBuf* b : all) b->release();
     FirstLayer* fl[] = {&det_first, &ref_first};
@@ -1418,6 +1419,42 @@ int dcu_refinenet_metrics(DcuEngine* e, const float* heat_pred_dev, const int32_
   launch_heat_argmax_dist(heat_pred_dev, corners_pred_dev, heat_target_dev, p, 64, 64, dist_dev, (cudaStream_t)stream);
   if (p > 0) e->launches++;
   CK(cudaGetLastError());
+  return DCU_OK;
+}
+
+int dcu_synth_frames(DcuEngine* e, const DcuSynthFrame* params_host, int n, uint64_t seed, int first_index, const uint8_t* board_dev,
+                     int board_px, uint8_t* frames_dev, void* stream) {
+  if (!e || !params_host || !board_dev || !frames_dev || n < 0 || board_px < 2 || first_index < 0)
+    return fail(DCU_ERR_INVALID, "dcu_synth_frames: bad argument");
+  if (n == 0) return DCU_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int H = e->cfg.height, W = e->cfg.width;
+  const int lat_cap = (H / 4 + 3) * (W / 4 + 3);
+  for (int i = 0; i < n; ++i) {
+    const DcuSynthFrame& P = params_host[i];
+    if (P.lat_step < 4 || P.lat_h != H / P.lat_step + 3 || P.lat_w != W / P.lat_step + 3 || P.n_boards < 0 || P.n_boards > 4)
+      return fail(DCU_ERR_INVALID, "dcu_synth_frames: bad frame parameters (lattice step >= 4, lattice size H/step+3 x W/step+3, <= 4 boards)");
+  }
+  if (e->synth_params.bytes < (size_t)n * sizeof(DcuSynthFrame)) { e->synth_params.release(); CK(e->synth_params.alloc((size_t)n * sizeof(DcuSynthFrame))); }
+  if (e->synth_lat.bytes < (size_t)n * lat_cap) { e->synth_lat.release(); CK(e->synth_lat.alloc((size_t)n * lat_cap)); }
+  CK(cudaMemcpyAsync(e->synth_params.p, params_host, (size_t)n * sizeof(DcuSynthFrame), cudaMemcpyHostToDevice, s));
+  CK(launch_synth_frames(e->synth_params.as<DcuSynthFrame>(), board_dev, board_px, e->synth_lat.as<uint8_t>(), lat_cap, seed, first_index, n, H, W,
+                         frames_dev, s));
+  e->launches += 2;
+  return DCU_OK;
+}
+
+int dcu_warp_perspective_u8(DcuEngine* e, const uint8_t* src_dev, int src_h, int src_w, const double* minv9_host, uint8_t* dst_dev, int dst_h,
+                            int dst_w, void* stream) {
+  if (!e || !src_dev || !minv9_host || !dst_dev || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1 || src_h > 32767 || src_w > 32767)
+    return fail(DCU_ERR_INVALID, "dcu_warp_perspective_u8: bad argument");
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (e->synth_m.bytes < 72) CK(e->synth_m.alloc(72));
+  CK(cudaMemcpyAsync(e->synth_m.p, minv9_host, 72, cudaMemcpyHostToDevice, s));
+  CK(launch_warp_perspective_u8(src_dev, src_h, src_w, e->synth_m.as<double>(), dst_dev, dst_h, dst_w, s));
+  e->launches++;
   return DCU_OK;
 }
 

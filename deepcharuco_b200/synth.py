@@ -72,3 +72,161 @@ def tile_frames(frames, n):
     """Cycle a small pool of distinct frames up to n (benchmarks; generation cost stays bounded)."""
     reps = (n + len(frames) - 1) // len(frames)
     return np.ascontiguousarray(np.concatenate([frames] * reps, 0)[:n])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Frames generated ON THE DEVICE (SURVEY.md 8f row 4; csrc/synth.cu).  The host only derives the per-frame parameters
+# (a few hundred bytes per frame, vectorised over the batch); warp, paste, blur, gain and noise are one kernel launch.
+# ---------------------------------------------------------------------------------------------------------------------
+_STREAM_PARAMS = 1
+_BLUR_R = 6
+_PH_M0, _PH_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+
+
+def _philox4x32(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al., SC'11) on uint32 arrays; the same generator csrc/synth.cu runs per lattice node / pixel."""
+    c0, c1, c2, c3 = np.broadcast_arrays(*[np.asarray(c, np.uint32) for c in (c0, c1, c2, c3)])
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = c0.astype(np.uint64) * _PH_M0
+        p1 = c2.astype(np.uint64) * _PH_M1
+        hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), p0.astype(np.uint32)
+        hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), p1.astype(np.uint32)
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint32(k0), lo1, hi0 ^ c3 ^ np.uint32(k1), lo0
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def gpu_frame_params(n, H, W, seed, n_boards=None, first_index=0, base=240):
+    """Per-frame parameters of the device generator for frames first_index .. first_index + n - 1 of stream `seed`:
+    a dict of arrays (lat_step, bg_lo, bg_hi, gain, blur_w (n,13), H / Hinv (n,nb,3,3): board px -> frame px and back,
+    corners (n,nb,16,2): the projected inner corners = the frames' ground-truth labels, id = index 0..15)."""
+    if n_boards is None:
+        n_boards = 1 if (H <= 240 and W <= 320) else 4
+    assert 0 <= n_boards <= 4
+    idx = (first_index + np.arange(n)).astype(np.uint32)
+    k0, k1 = int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF
+    r = np.stack([np.stack(_philox4x32(np.uint32(j), idx, np.uint32(_STREAM_PARAMS), np.uint32(0), k0, k1), 1) for j in range(16)], 1)
+    u = r.reshape(n, 64).astype(np.float64) / 4294967296.0
+    p = dict(n_boards=n_boards)
+    sigma_bg = 1.0 + 5.0 * u[:, 0]
+    p["lat_step"] = np.maximum(4, np.rint(4.0 * sigma_bg)).astype(np.int32)
+    p["bg_lo"] = np.floor(80.0 * u[:, 1]).astype(np.float32)
+    p["bg_hi"] = (120.0 + np.floor(136.0 * u[:, 2])).astype(np.float32)
+    sigma = 0.3 + 1.2 * u[:, 3]
+    taps = np.exp(-0.5 * (np.arange(-_BLUR_R, _BLUR_R + 1)[None, :] / sigma[:, None]) ** 2)
+    p["blur_w"] = (taps / taps.sum(1, keepdims=True)).astype(np.float32)
+    p["gain"] = (0.3 + 0.8 * u[:, 4]).astype(np.float32)
+    Hs = np.zeros((n, n_boards, 3, 3)); Hi = np.zeros((n, n_boards, 3, 3)); corners = np.zeros((n, n_boards, 16, 2))
+    g = np.array(np.meshgrid(np.arange(1, 5), np.arange(1, 5))).reshape(2, -1).T * (base / 5.0)     # aruco_utils.py:122-131
+    g1 = np.concatenate([g, np.ones((16, 1))], 1)
+    src = np.array([[0, 0], [base - 1, 0], [base - 1, base - 1], [0, base - 1]], np.float64)
+    sq0 = np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]], np.float64)
+    for b in range(n_boards):
+        v = u[:, 8 + 12 * b: 8 + 12 * (b + 1)]
+        side = (0.3 + 0.6 * v[:, 0]) * base
+        ang = 2.0 * np.pi * v[:, 1]
+        if n_boards == 1:
+            cx, cy = W / 2 + (v[:, 2] * 0.4 - 0.2) * W, H / 2 + (v[:, 3] * 0.4 - 0.2) * H
+        else:
+            cx, cy = (0.15 + 0.7 * v[:, 2]) * W, (0.15 + 0.7 * v[:, 3]) * H
+        c, s = np.cos(ang), np.sin(ang)
+        rot = np.stack([np.stack([c, -s], 1), np.stack([s, c], 1)], 1)                               # (n,2,2)
+        dst = np.einsum("kj,nij->nki", sq0, rot) * (side / 2)[:, None, None] + np.stack([cx, cy], 1)[:, None, :]
+        dst = dst + (v[:, 4:12].reshape(n, 4, 2) * 0.16 - 0.08) * side[:, None, None]
+        A = np.zeros((n, 8, 8)); rhs = np.zeros((n, 8))
+        for i in range(4):
+            x, y = src[i]
+            A[:, i, 0], A[:, i, 1], A[:, i, 2] = x, y, 1.0
+            A[:, i, 6], A[:, i, 7] = -x * dst[:, i, 0], -y * dst[:, i, 0]
+            A[:, i + 4, 3], A[:, i + 4, 4], A[:, i + 4, 5] = x, y, 1.0
+            A[:, i + 4, 6], A[:, i + 4, 7] = -x * dst[:, i, 1], -y * dst[:, i, 1]
+            rhs[:, i], rhs[:, i + 4] = dst[:, i, 0], dst[:, i, 1]
+        h = np.linalg.solve(A, rhs[:, :, None])[:, :, 0]
+        Hm = np.concatenate([h, np.ones((n, 1))], 1).reshape(n, 3, 3)
+        Hs[:, b] = Hm
+        Hi[:, b] = np.linalg.inv(Hm)
+        q = np.einsum("kj,nij->nki", g1, Hm)
+        corners[:, b] = q[:, :, :2] / q[:, :, 2:3]
+    p["H"], p["Hinv"], p["corners"] = Hs, Hi, corners
+    return p
+
+
+def pack_frame_params(p, H, W):
+    """dict of arrays -> ctypes array of DcuSynthFrame."""
+    from . import _native as N
+    n = len(p["lat_step"])
+    arr = (N.DcuSynthFrame * n)()
+    raw = np.frombuffer(arr, dtype=np.uint8).reshape(n, -1)
+    rec = np.zeros(n, dtype=np.dtype([("lat", np.int32, 4), ("f", np.float32, 4), ("w", np.float32, 16), ("h", np.float64, (4, 9))]))
+    assert rec.dtype.itemsize == raw.shape[1]
+    rec["lat"][:, 0] = p["lat_step"]
+    rec["lat"][:, 1] = H // p["lat_step"] + 3
+    rec["lat"][:, 2] = W // p["lat_step"] + 3
+    rec["lat"][:, 3] = p["n_boards"]
+    rec["f"][:, 0], rec["f"][:, 1], rec["f"][:, 2] = p["bg_lo"], p["bg_hi"], p["gain"]
+    rec["w"][:, :2 * _BLUR_R + 1] = p["blur_w"]
+    rec["h"][:, :p["n_boards"]] = p["Hinv"].reshape(n, p["n_boards"], 9)
+    raw[:] = rec.view(np.uint8).reshape(n, -1)
+    return arr
+
+
+_GPU_STATE = {}
+
+
+def make_frames_gpu(n, H=240, W=320, seed=0, n_boards=None, first_index=0, device=0, return_device=False):
+    """(n, H, W) uint8 frames generated on the B200 + their ground-truth corners (n, n_boards, 16, 2) float64 (ids 0..15).
+    Deterministic in (seed, first_index + i, H, W, n_boards) -- frame i does not depend on n.  return_device: a CUDA tensor."""
+    import torch
+    from . import _native as N
+    from .inference import _scratch_context
+    p = gpu_frame_params(n, H, W, seed, n_boards, first_index)
+    dev = torch.device("cuda", int(device))
+    key = (int(device),)
+    if key not in _GPU_STATE:
+        _GPU_STATE[key] = torch.from_numpy(np.ascontiguousarray(board_render(240))).to(dev)
+    board = _GPU_STATE[key]
+    eng = _scratch_context(16, int(device)).engine(H, W)
+    frames = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
+    arr = pack_frame_params(p, H, W)
+    s = torch.cuda.current_stream(dev)
+    N.check(N.lib().dcu_synth_frames(eng.handle, arr, n, int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_index), board.data_ptr(), 240,
+                                     frames.data_ptr(), s.cuda_stream))
+    s.synchronize()          # `arr` (host) is read by an asynchronous copy
+    return (frames if return_device else frames.cpu().numpy()), p["corners"]
+
+
+def corner_labels(corners, H, W):
+    """Ground-truth label keypoints per frame in the reference's format (inference.py:150-152): rows [x, y, id] sorted by id, for
+    the corners that fall inside the frame (first board only carries the ids the reference's labels use)."""
+    out = []
+    for c in corners:
+        rows = []
+        for b in range(c.shape[0]):
+            for k in range(16):
+                x, y = c[b, k]
+                if 0 <= x < W and 0 <= y < H:
+                    rows.append([x, y, float(k)])
+        rows.sort(key=lambda r: r[2])
+        out.append(np.array(rows, np.float64).reshape(-1, 3))
+    return out
+
+
+def warp_perspective_u8_gpu(src_u8, M, dsize, device=0):
+    """cv2.warpPerspective(src, M, dsize, flags=cv2.INTER_LINEAR) for one uint8 single-channel image, on the B200 (bit-exact)."""
+    import cv2
+    import torch
+    from . import _native as N
+    from .inference import _scratch_context
+    Wd, Hd = dsize
+    src = np.ascontiguousarray(src_u8, np.uint8)
+    minv = np.ascontiguousarray(cv2.invert(np.asarray(M, np.float64))[1], np.float64)       # what cv2 does internally
+    dev = torch.device("cuda", int(device))
+    d_src = torch.from_numpy(src).to(dev)
+    dst = torch.empty((Hd, Wd), dtype=torch.uint8, device=dev)
+    eng = _scratch_context(16, int(device)).engine(240, 320)
+    s = torch.cuda.current_stream(dev)
+    N.check(N.lib().dcu_warp_perspective_u8(eng.handle, d_src.data_ptr(), src.shape[0], src.shape[1], minv.ctypes.data, dst.data_ptr(),
+                                            Hd, Wd, s.cuda_stream))
+    s.synchronize()
+    return dst.cpu().numpy()

@@ -205,6 +205,32 @@ int dcu_pixel_error(DcuEngine* e, const int32_t* counts_dev, const int32_t* offs
                     int n, const int32_t* tcounts_dev, const int32_t* toffsets_dev, const double* target_dev, int32_t* status_dev,
                     double* out_dev, void* stream);
 
+/* ---- synthetic frames on the device ----
+ * What the reference's data path does per training / validation sample on the host (transformations.py:22-52,105-114,
+ * custom_aug.PasteBoard: warp the rendered board, paste it on a background, blur, brightness, noise), as one launch per batch.
+ * Per-frame parameters come from the host (deepcharuco_b200/synth.py: gpu_frame_params -- homographies and Gaussian taps need
+ * float64 trigonometry / a linear solve); the per-pixel work is the kernel's: OpenCV's own fixed-point bilinear warp of the board
+ * texture and its mask (bit-exact with cv2.warpPerspective on u8, INTER_LINEAR, BORDER_CONSTANT), a lattice-noise background,
+ * a separable 13-tap blur with reflect-101 borders, gain, and Philox4x32-10 noise: frame i depends only on (seed, first_index + i). */
+typedef struct DcuSynthFrame {
+  int32_t lat_step, lat_h, lat_w;   /* background lattice: spacing in pixels, lattice size (H / step + 3, W / step + 3) */
+  int32_t n_boards;                 /* 0..4 boards pasted in order */
+  float bg_lo, bg_hi, gain, reserved;
+  float blur_w[16];                 /* 13 normalised taps (-6..6), float32 */
+  double hinv[4][9];                /* per board: frame pixel -> board pixel homography (row-major 3x3), what cv2.warpPerspective
+                                       computes internally as invert(M) */
+} DcuSynthFrame;
+
+/* params_host [n] (host memory, copied inside), board_dev uint8 [board_px][board_px] (the rendered board, device),
+ * frames_dev uint8 [n][H][W] (device) with H, W the engine's frame size. */
+int dcu_synth_frames(DcuEngine* e, const DcuSynthFrame* params_host, int n, uint64_t seed, int first_index,
+                     const uint8_t* board_dev, int board_px, uint8_t* frames_dev, void* stream);
+
+/* cv2.warpPerspective(src, M, (dst_w, dst_h), flags=INTER_LINEAR, borderMode=BORDER_CONSTANT, 0) for one uint8 single-channel image
+ * with minv9_host = invert(M) (float64, row-major; host memory): src_dev [src_h][src_w] -> dst_dev [dst_h][dst_w], bit-exact. */
+int dcu_warp_perspective_u8(DcuEngine* e, const uint8_t* src_dev, int src_h, int src_w, const double* minv9_host,
+                            uint8_t* dst_dev, int dst_h, int dst_w, void* stream);
+
 /* RefineNet validation metric on the device: the per-sample part of Refinenet_Metrics.update (models/metrics.py:141-158):
  * dist[i] = L2 distance in heat-map pixels between the arg-max of the predicted 64x64 heat map and the arg-max of the target map
  * (first maximum of the flattened map).  The prediction is either a heat map tensor heat_pred_dev [p][64][64] or, when that is

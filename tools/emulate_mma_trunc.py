@@ -46,6 +46,8 @@ def to_f32(x64, mode):
 def conv_model(x, w, pad, mode, seg, taps_collapsed=None):
     """x (N,C,H,W) fp32, w (O,C,3,3) fp32 -> conv output (N,O,H',W') fp32 before bias, per the kernel's MMA order."""
     O, C = w.shape[0], w.shape[1]
+    if isinstance(seg, dict):            # per-layer policy: MMAs per segment by input channel count
+        seg = seg.get(C, 0)
     mx = float(w.abs().max())
     s = 2.0 ** np.floor(np.log2(32768.0 / mx))
     xh, xl = split_f16(x)
@@ -137,7 +139,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=2)
     ap.add_argument("--modes", default="rz,rn")
-    ap.add_argument("--segs", default="0,9,3")
+    ap.add_argument("--segs", default="0,9,3", help="MMAs per segment; 'a:b' = a for 64-channel inputs, b for 128-channel inputs")
     ap.add_argument("--patches", type=int, default=12)
     ap.add_argument("--skip-det", action="store_true")
     a = ap.parse_args()
@@ -153,7 +155,7 @@ if __name__ == "__main__":
         P = torch.from_numpy(np.concatenate(P))[: a.patches, None]
         h0 = oracle.refinenet_forward(sr, P)
         for mode in a.modes.split(","):
-            for seg in [int(s) for s in a.segs.split(",")]:
+            for seg in [({64: int(s.split(":")[0]), 128: int(s.split(":")[1])} if ":" in s else int(s)) for s in a.segs.split(",")]:
                 if not a.skip_det:
                     loc, ids = det(x, mode, seg)
                     print(f"mode={mode} seg={seg}: dloc {float((loc - loc0).abs().max()):.3e} dids {float((ids - ids0).abs().max()):.3e} "
