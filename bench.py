@@ -141,6 +141,78 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def other_configs(dc, Nn, synth, deepc, refinenet, eng, peaks, torch):
+    """The other BASELINE.json configs on this GPU (device-resident inputs, CUDA events, 2 warm-ups): 1 = one frame per call through
+    the drop-in infer_image (src/benchmark.py:38-53), 2 = detector only at batch 64, 4 = RefineNet on 16384 patches, 5 = one GPU's
+    shard (256 frames) of the 2048 x 640x480 batch.  frac = algorithmic TFLOP/s / measured sustained bf16 peak."""
+    L = Nn.lib()
+    peak = peaks["bf16_sustained"]
+    out = {}
+
+    def timed(fn, iters):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    # config 1: the reference's own benchmark loop on its sample image (BGR u8, one frame per call, results on the host)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sample_image.npz"))
+    img = g["bgr"]
+    for _ in range(5):
+        kp, _ = dc.infer_image(img, 16, deepc, refinenet, draw_pred=False)
+    t0 = time.perf_counter()
+    calls = 300
+    for _ in range(calls):
+        kp, _ = dc.infer_image(img, 16, deepc, refinenet, draw_pred=False)
+    dt = time.perf_counter() - t0
+    out["1_single_frame_infer_image"] = dict(calls_per_s=calls / dt, ms_per_call=dt / calls * 1e3, corners=int(kp.shape[0]),
+                                             matches_reference_golden=bool(np.abs(kp - g["out_refined"]).max() <= 1e-3),
+                                             note="src/benchmark.py:38-53 loop through the drop-in infer_image; reference README: > 200 fps on a GTX 1080 Ti")
+    # config 2: detector forward only, batch 64
+    frames = torch.from_numpy(synth.tile_frames(synth.make_frames(64, seed=1), 64)).cuda()
+    loc = torch.empty((64, 65, 30, 40), device="cuda"); ids = torch.empty((64, 17, 30, 40), device="cuda")
+    ms = timed(lambda: Nn.check(L.dcu_detector_forward(eng.handle, frames.data_ptr(), 64, loc.data_ptr(), ids.data_ptr(), None)), 10)
+    tf = 64 * eng.detector_flops_per_frame() / ms / 1e9
+    out["2_detector_b64_320x240"] = dict(ms=ms, frames_per_s=64 / ms * 1e3, tflops_alg=tf, frac=tf / peak)
+    # decode + gather as a stand-alone stage on fp32 logits (the HBM-bound kernel of SURVEY 8d)
+    counts = torch.empty(64, dtype=torch.int32, device="cuda"); offs = torch.empty(64, dtype=torch.int32, device="cuda")
+    tot = torch.zeros(1, dtype=torch.int32, device="cuda"); kpt = torch.empty((eng.max_patches, 4), dtype=torch.int32, device="cuda")
+    pt = torch.empty((eng.max_patches, 24, 24), device="cuda")
+    ms = timed(lambda: Nn.check(L.dcu_decode_gather(eng.handle, loc.data_ptr(), ids.data_ptr(), frames.data_ptr(), 64, 16, 0, counts.data_ptr(),
+                                                    offs.data_ptr(), tot.data_ptr(), kpt.data_ptr(), pt.data_ptr(), None)), 20)
+    k2 = int(tot.item())
+    nbytes = 64 * 82 * 1200 * 4 + k2 * (2304 + 2304 + 16)
+    out["decode_stage_b64"] = dict(ms=ms, gb_per_s_alg=nbytes / ms / 1e6, frac_hbm=nbytes / ms / 1e6 / peaks["hbm"], corners=k2,
+                                   note="64 frames = 25 MB of logits: launch-latency dominated at this size")
+    # config 4: RefineNet on 16384 real patches (the gather output above, cycled)
+    own4 = eng.max_patches < 16384
+    e4 = Nn.Engine(deepc._ctx.state_det, deepc._ctx.state_ref, 240, 320, 16, eng.device, max_batch=8, max_patches=16384) if own4 else eng
+    reps = (16384 + k2 - 1) // max(k2, 1)
+    pt16 = pt[:k2].repeat(reps, 1, 1)[:16384].contiguous(); kp16 = kpt[:k2].repeat(reps, 1)[:16384].contiguous()
+    corners = torch.empty((16384, 2), dtype=torch.int32, device="cuda"); refined = torch.empty((16384, 2), device="cuda")
+    ms = timed(lambda: Nn.check(L.dcu_refine_forward(e4.handle, pt16.data_ptr(), kp16.data_ptr(), 4, 16384, corners.data_ptr(),
+                                                     refined.data_ptr(), None, None)), 5)
+    tf = 16384 * e4.refine_flops_per_patch() / ms / 1e9
+    out["4_refinenet_16384_patches"] = dict(ms=ms, patches_per_s=16384 / ms * 1e3, tflops_alg=tf, frac=tf / peak)
+    if own4:
+        e4.close()
+    # config 5: one GPU's shard of the 2048 x 640x480 batch (256 frames, 4 boards per frame)
+    e5 = Nn.Engine(deepc._ctx.state_det, deepc._ctx.state_ref, 480, 640, 16, eng.device, max_batch=256, max_patches=32768)
+    f5 = torch.from_numpy(synth.tile_frames(synth.make_frames(16, 480, 640, seed=1), 256)).cuda()
+    ms = timed(lambda: e5.infer_batch_device(f5.data_ptr(), 256, 16, True, None), 3)
+    k5 = int(e5._dev_out["total"].item())
+    tf = (256 * e5.detector_flops_per_frame() + k5 * e5.refine_flops_per_patch()) / ms / 1e9
+    out["5_full_b256_640x480_per_gpu"] = dict(ms=ms, frames_per_s=256 / ms * 1e3, corners=k5, tflops_alg=tf, frac=tf / peak)
+    e5.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -150,6 +222,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step (BASELINE config 3: 256)")
     ap.add_argument("--conv", default=os.environ.get("DCU_CONV_IMPL", ""), help="ffma | tcgen05 (default: library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (1, 2, 4, 5) reported next to the headline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -168,6 +241,13 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        # one slice of the host cores per rank: the ranks' copy / launch threads do not migrate onto each other's cores
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]) or set(cores))
+        except (AttributeError, OSError):
+            pass
     if args.conv:
         os.environ["DCU_CONV_IMPL"] = args.conv
 
@@ -233,6 +313,41 @@ def main():
     h2d = B * H * W
     d2h = 4 + 2 * B * 4 + total_k * (16 + 8)
 
+    # the same through the PYTHON surface a user of the reference switches to: dc.infer_batch (host ndarray in, list of per-frame
+    # (K,3) float64 arrays out, incl. the marshalling of inference.py:68-70)
+    py_steps = max(3, args.steps // 3)
+
+    def step_python(i):
+        return dc.infer_batch(host_batches[i % R].numpy(), 16, deepc, refinenet)
+    step_python(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(py_steps):
+        step_python(i)
+    torch.cuda.synchronize()
+    dt_py = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt_py, op=dist.ReduceOp.MAX)
+    e2e_python = world * B * py_steps / float(dt_py.item())
+
+    # N > 1: ONE host batch of world x B frames through the user-facing multi-GPU call (every rank holds the batch, runs its
+    # shard, results all-gathered over NCCL so every rank returns the full list): scatter + pipeline + merge inside the timed region
+    one_batch = None
+    if world > 1:
+        big = np.concatenate([hb.numpy() for hb in host_batches[:min(world, R)]] * ((world + R - 1) // R), 0)[:world * B]
+        dc.infer_batch_distributed(big, 16, deepc, refinenet)
+        barrier()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            full = dc.infer_batch_distributed(big, 16, deepc, refinenet)
+        torch.cuda.synchronize()
+        dt_ob = torch.tensor([time.perf_counter() - t0], device=dev)
+        dist.all_reduce(dt_ob, op=dist.ReduceOp.MAX)
+        one_batch = dict(frames=int(world * B), value=world * B * reps / float(dt_ob.item()), unit=UNIT, ms_per_batch=float(dt_ob.item()) / reps * 1e3,
+                         api="infer_batch_distributed (same host batch on every rank, own shard per rank, packed results all-gathered over NCCL)",
+                         frames_returned=len(full))
+
     # roofline of the dominant kernel (3x3 conv): per-launch CUDA events on the launching stream, over 2 more steps
     eng.profile_enable(True)
     for i in range(2):
@@ -253,9 +368,10 @@ def main():
     # DRAM traffic of the dominant kernel: from the committed ncu capture of this same workload (per-launch average)
     conv_traffic, traffic_src = None, None
     try:
-        ls = json.load(open(os.path.join(ROOT, "profiles", "r1_launch_summary.json")))
+        ls = json.load(open(os.path.join(ROOT, "profiles", "r2_launch_summary.json")))
         conv_traffic = ls["conv3x3_tc"]["dram_bytes_per_launch"]
-        traffic_src = "profiles/r1_launch_summary.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, average per launch)"
+        traffic_src = ("profiles/r2_launch_summary.json: ncu dram__bytes_read.sum + dram__bytes_write.sum of THIS workload (tools/profile_step.py "
+                       "--batch 256), average per conv_tc2_kernel launch")
     except Exception:
         pass
     if rank == 0:
@@ -272,6 +388,8 @@ def main():
             clocks=clocks,
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                      ms_per_step=ms_e2e / args.steps, api="dcu_infer_batch_host (pinned host u8 frames in, packed keypoints out)"),
+            e2e_python=dict(value=e2e_python, unit=UNIT, steps=py_steps,
+                            api="deepcharuco_b200.infer_batch (host ndarray in, list of per-frame (K,3) float64 arrays out)"),
             gpu_launches=int(launches),
             roofline=dict(bound="tensor", kernel="conv_tc2_kernel (CTA-pair tcgen05 3x3 convolution; all 3x3 layer shapes of both networks, aggregated over launches)",
                           achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s", frac=achieved_tf / peak_tf if peak_tf else None,
@@ -283,12 +401,18 @@ def main():
                           issued_frac=(issued_tf / peak_tf) if (peak_tf and issued_tf) else None,
                           traffic=conv_traffic, traffic_source=traffic_src, launches=int(conv_n), kernel_ms_per_step=conv_ms / 2,
                           share_of_step=conv_ms / step_ms_prof if step_ms_prof else None,
-                          decode_gather=dict(bound="hbm", achieved=(dec_bytes / (dec_ms / 1e3) / 1e9) if dec_ms > 0 else 0.0,
-                                             peak=peaks["hbm"], unit="GB/s", launches=int(dec_n), kernel_ms_per_step=dec_ms / 2,
-                                             note="SURVEY 8d bytes (82 logit planes + patches).  In this pipeline the per-cell arg-max is taken in "
-                                                  "the 1x1 head epilogues (DCU_ARG_HEADS), so the logits are neither written nor re-read: the "
-                                                  "kernel that is left reads 2 B per cell and gathers the patches")),
+                          decode_gather=dict(bound="hbm", logit_read="eliminated", launches=int(dec_n), kernel_ms_per_step=dec_ms / 2,
+                                             actual_bytes_per_step=int(B * 1200 * 2 + total_k * (2304 + 2304 + 16)),
+                                             survey_bytes_per_step=int(dec_bytes / 2),
+                                             note="the per-cell arg-max is taken in the 1x1 head epilogues, so the 82 logit planes of SURVEY 8d "
+                                                  "(393.6 kB / frame) are neither written nor re-read: the kernel that is left reads 2 B per cell + the "
+                                                  "patch windows and is launch-latency bound (no GB/s figure is meaningful); the stand-alone stage "
+                                                  "dcu_decode_gather on fp32 logits is timed under configs.decode_stage")),
         )
+        if one_batch is not None:
+            line["one_batch"] = one_batch
+        if not args.no_configs and world == 1:
+            line["configs"] = other_configs(dc, Nn, synth, deepc, refinenet, eng, peaks, torch)
         if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (the other ranks would be spinning on the barrier)
             fps, cores, done, dt = cpu_reference_fps(pool[:32], seconds_budget=15.0)
             line["cpu_baseline"] = dict(value=fps, unit=UNIT, cores=cores, kind="port",

@@ -808,9 +808,9 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
   g.out = p.out_layout.plane ? p.out_layout
                              : (p.pool ? h2_standard(p.cout_total, p.hout >> 1, p.wout >> 1) : h2_standard(p.cout_total, p.hout, p.wout));
   g.slices = n_slices;
-  // chunks per segment: layers with 4 chunks (64 input channels) have ~8k-cycle tiles and afford two drains of 2k cycles each;
-  // 8-chunk layers drain every chunk
-  static const int seg_c64 = [] { const char* v = getenv("DCU_SEG_CHUNKS64"); return v ? atoi(v) : 2; }();
+  // chunks per segment (default 1 = a drain per 16-channel chunk; measured on B200, batch 256: 1/1 -> max |dloc| 0.0088 at 15.2 k
+  // frames/s, 2/1 -> 0.019 at 15.6 k, 2/2 -> 0.021 at 15.9 k, off -> 0.055 at 17.3 k)
+  static const int seg_c64 = [] { const char* v = getenv("DCU_SEG_CHUNKS64"); return v ? atoi(v) : 1; }();
   static const int seg_c128 = [] { const char* v = getenv("DCU_SEG_CHUNKS128"); return v ? atoi(v) : 1; }();
   static const int seg_first = [] { const char* v = getenv("DCU_SEG_FIRST"); return v ? atoi(v) : 0; }();
   g.segc = std::max(1, std::min(p.cin <= 64 ? seg_c64 : seg_c128, p.cin / 16));
@@ -847,12 +847,13 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
 
 int tc2_block_bytes(int nt) { return 48 * nt; }
 // two-level accumulation (SEG template parameter) is the default; DCU_SEG=0 keeps whole-tile accumulation chains in tensor memory
-// DCU_SEG: 0 = whole-tile accumulation chains in tensor memory everywhere, 1 = two-level accumulation on every layer,
-// 2 = on the layers with >= 128 input channels only (chains of 72 MMAs; their tiles are long enough to hide the extra drains).
+// DCU_SEG: 0 (default) = whole-tile accumulation chains in tensor memory, 1 = two-level accumulation on every layer ("strict":
+// max |dloc| 0.0088 instead of 0.055 at - 12 % frames/s; every drain re-reads 128 TMEM columns per m-tile at 64 B / cycle / SM,
+// which is what it costs), 2 = on the layers with >= 128 input channels only.  Chunks per segment: DCU_SEG_CHUNKS64 / _CHUNKS128.
 // Read per call: tests switch it between engines of one process.
 int tc2_seg_policy() {
   const char* v = getenv("DCU_SEG");
-  return v ? atoi(v) : 1;
+  return v ? atoi(v) : 0;
 }
 bool tc2_segmented(int cin) {
   const int pol = tc2_seg_policy();

@@ -40,11 +40,36 @@ def unpack_results(counts, flat, integer=False):
     return out
 
 
+def _gather_packed(counts, flat, world, rank, group, device):
+    """All-gather per-rank (counts int64 [n_r], rows float64 [k_r, 3]) as TENSORS (NCCL moves CUDA tensors, gloo CPU tensors):
+    sizes first, then the payloads padded to the largest shard.  ~24 B per corner: a few hundred kB for a 2048-frame batch."""
+    import torch
+    import torch.distributed as dist
+    sizes = torch.tensor([counts.shape[0], flat.shape[0]], dtype=torch.int64, device=device)
+    all_sizes = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = torch.stack(all_sizes).cpu().numpy()
+    n_max, k_max = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
+    buf = torch.zeros(n_max + 3 * k_max, dtype=torch.float64, device=device)
+    buf[:counts.shape[0]] = torch.from_numpy(counts.astype(np.float64)).to(device)
+    if flat.shape[0]:
+        buf[n_max:n_max + 3 * flat.shape[0]] = torch.from_numpy(np.ascontiguousarray(flat).reshape(-1)).to(device)
+    out = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    res = []
+    for r in range(world):
+        b = out[r].cpu().numpy()
+        n_r, k_r = int(all_sizes[r, 0]), int(all_sizes[r, 1])
+        res.append((b[:n_r].astype(np.int64), b[n_max:n_max + 3 * k_r].reshape(k_r, 3)))
+    return res
+
+
 def infer_batch_distributed(frames, dust_bin_ids, deepc=None, refinenet=None, group=None, local_fn=None):
     """Multi-GPU `infer_batch` for one process per GPU (torchrun / torch.distributed): every rank passes the SAME (N,H,W)
     uint8 batch, runs its contiguous shard on its own device and engine, and the per-frame results (tiny: 24 B per corner) are
-    all-gathered as packed arrays, so every rank returns the full list in frame order.  No collective touches the data path
+    all-gathered as packed tensors, so every rank returns the full list in frame order.  No collective touches the data path
     (SURVEY.md 8e); the gather moves results only.  `local_fn(frames_shard) -> list` replaces the engine call in CPU tests."""
+    import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -56,6 +81,8 @@ def infer_batch_distributed(frames, dust_bin_ids, deepc=None, refinenet=None, gr
     integer = refinenet is None and deepc is not None
     if world == 1:
         return list(mine)
-    gathered = [None] * world
-    dist.all_gather_object(gathered, pack_results(mine), group=group)
+    backend = dist.get_backend(group)
+    device = torch.device("cuda", deepc._ctx.device if deepc is not None else torch.cuda.current_device()) if "nccl" in str(backend) else torch.device("cpu")
+    counts, flat = pack_results(mine)
+    gathered = _gather_packed(counts, flat, world, rank, group, device)
     return merge_shards([unpack_results(c, f, integer=integer) for c, f in gathered])

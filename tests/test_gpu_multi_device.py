@@ -29,3 +29,19 @@ def test_two_devices_in_one_process():
     one = dc.infer_batch(frames[:1], 16, *m1)[0]
     one = dc.infer_batch(frames[:1], 16, *m1)[0]
     assert np.array_equal(one, a[0])
+
+
+def test_infer_batch_distributed_under_nccl():
+    """One process per GPU (torchrun, NCCL backend): the user-facing multi-GPU call returns, on every rank, exactly what one GPU
+    returns for the whole batch (tools/dist_check.py).  Needs two GPUs."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29600 + (os.getpid() % 300)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(root, "tools", "dist_check.py")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_CHECK OK" in r.stdout, r.stdout[-3000:]

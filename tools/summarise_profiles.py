@@ -72,15 +72,41 @@ KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__registers_p
         "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum"]
-for rep, name in (("conv_tc.ncu-rep", "ncu_conv_tc2.txt"), ("small.ncu-rep", "ncu_small_kernels.txt")):
+for rep, name in (("conv_tc.ncu-rep", "ncu_conv_tc2.txt"), ("small.ncu-rep", "ncu_small_kernels.txt"), ("conv1b.ncu-rep", "ncu_conv1b.txt"),
+                  ("step_full_raw.csv", "ncu_step_full.txt")):
     if not os.path.isfile(G(rep)):
         continue
-    raw = subprocess.run(["ncu", "-i", G(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rr = list(csv.reader(raw.splitlines()))
+    if rep.endswith(".csv"):          # raw page exported on the GPU box (the report itself stays there)
+        raw = open(G(rep)).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", G(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader([l for l in raw.splitlines() if not l.startswith("==")]))
     hdr, units = rr[0], rr[1]
     with open(P(name), "w") as f:
-        f.write(f"ncu --set full --clock-control none --import-source on ({tag}); one block per captured launch.\n"
-                f"Workload: tools/profile_step.py (bench workload; conv capture uses 32 frames = one full-resolution micro-batch).\n\n")
+        f.write(f"ncu --set full --clock-control none ({tag}); one block per captured launch.\n"
+                f"Workload: ONE step of the bench workload (tools/profile_step.py --batch 256: 256 frames 320x240, engine defaults), profiled after a warm step.\n\n")
+        if rep.endswith(".csv"):
+            # per-instantiation table: launches, total time, tensor-pipe and DRAM utilisation (time-weighted)
+            tab = collections.OrderedDict()
+            for r in rr[2:]:
+                d = dict(zip(hdr, r))
+                def num(k):
+                    try:
+                        return float(d.get(k, "").replace(",", ""))
+                    except ValueError:
+                        return 0.0
+                t = num("gpu__time_duration.sum")
+                t = t / 1e3 if units[hdr.index("gpu__time_duration.sum")] == "ns" else (t * 1e3 if units[hdr.index("gpu__time_duration.sum")] == "ms" else t)
+                a = tab.setdefault(short(d.get("Kernel Name", "")), dict(n=0, us=0.0, tens=0.0, dram=0.0, l1=0.0))
+                a["n"] += 1; a["us"] += t
+                a["tens"] += t * num("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")
+                a["dram"] += t * num("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
+                a["l1"] += t * num("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed")
+            f.write(f"{'kernel instantiation':44s} {'launches':>8s} {'total us':>10s} {'tensor pipe %':>14s} {'DRAM %':>8s} {'smem operand fetch %':>21s}\n")
+            for k, a in sorted(tab.items(), key=lambda kv: -kv[1]["us"]):
+                u = max(a["us"], 1e-9)
+                f.write(f"{k[:44]:44s} {a['n']:8d} {a['us']:10.1f} {a['tens']/u:14.1f} {a['dram']/u:8.1f} {a['l1']/u:21.1f}\n")
+            f.write("\n")
         for r in rr[2:]:
             d = dict(zip(hdr, r))
             f.write(f"== {short(d.get('Kernel Name',''))}   grid {d.get('Grid Size','')}  block {d.get('Block Size','')}\n")
@@ -90,6 +116,8 @@ for rep, name in (("conv_tc.ncu-rep", "ncu_conv_tc2.txt"), ("small.ncu-rep", "nc
             f.write("\n")
 # ---- 3. copy the small text/JSON artefacts -------------------------------------------------------------------------------
 for src, dst in (("bench.json", "bench.json"), ("bench_reference.json", "bench_reference.json"), ("parity.json", "parity.json"),
+                 ("bench_strict.json", "bench_strict_accumulation.json"), ("parity_strict.json", "parity_strict_accumulation.json"),
+                 ("parity_640.json", "parity_640x480.json"), ("mma_probe.json", "mma_probe.json"), ("mma_probe.log", "mma_probe.txt"),
                  ("tcstats.log", "tc_role_cycles.txt"), ("tc_vs_ffma.log", "tc_vs_ffma.txt"), ("pytest.log", "pytest_gpu.txt"),
                  ("smoke.log", "smoke.txt")):
     if os.path.isfile(G(src)):
