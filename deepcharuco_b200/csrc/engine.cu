@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX 3: ranges per stage for nsys / ncu --nvtx; no-ops when no tool is attached
+
 #include "../../include/deepcharuco_b200.h"
 #include "common.cuh"
 
@@ -30,6 +32,11 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 namespace {
+
+struct NvtxRange {          // host-side range around the launches of one stage
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DevBuf {
   void* p = nullptr;
@@ -635,6 +642,7 @@ static int run_first(DcuEngine* e, const FirstLayer& f, const uint8_t* in_u8, co
 // detector on n <= mb2 frames: loc/ids NCHW out
 static int detector_group(DcuEngine* e, const uint8_t* frames, const float* images, int n, float* loc, float* ids,
                           cudaStream_t s) {
+  NvtxRange nvtx_range("dcu:detector");
   const int H = e->cfg.height, W = e->cfg.width;
   float* a0 = e->act[0].as<float>();
   float* a1 = e->act[1].as<float>();
@@ -732,6 +740,7 @@ static int detector_group(DcuEngine* e, const uint8_t* frames, const float* imag
 static int decode_group(DcuEngine* e, const float* loc, const float* ids, const uint8_t* frames, int n, int dust_bin,
                         int append, int32_t* counts, int32_t* offsets, int32_t* total, int32_t* kpts, float* patches,
                         cudaStream_t s) {
+  NvtxRange nvtx_range("dcu:decode_gather");
   DecodeParams d{};
   d.loc = loc; d.ids = ids; d.frames = frames; d.lut = e->lut.as<float>();
   if (e->arg_heads_now) { d.loc_arg = e->loc_arg.as<uint8_t>(); d.ids_arg = e->ids_arg.as<uint8_t>(); }
@@ -752,6 +761,7 @@ static int decode_group(DcuEngine* e, const float* loc, const float* ids, const 
 // RefineNet on p patches (any p; processed in chunks of rp)
 static int refine_run(DcuEngine* e, const float* patches, const int32_t* xy, int xy_stride, int p, int32_t* corners,
                       float* refined, float* heat, cudaStream_t s) {
+  NvtxRange nvtx_range("dcu:refinenet");
   float* a0 = e->act[0].as<float>();
   float* a1 = e->act[1].as<float>();
   int rc;
@@ -1307,6 +1317,7 @@ static int infer_small_graph(DcuEngine* e, const uint8_t* frames_host, int n, in
 static int infer_batch_host_impl(DcuEngine* e, const uint8_t* frames_host, int n, int channels, int dust_bin_ids, int use_refinenet,
                                  int32_t* counts_host, int32_t* offsets_host, int32_t* total_host, int32_t* kpts_host,
                                  float* refined_host, void* stream) {
+  NvtxRange nvtx_range("dcu:infer_batch_host");
   if (!e || !frames_host || !counts_host || !offsets_host || !total_host || !kpts_host || n < 0)
     return fail(DCU_ERR_INVALID, "dcu_infer_batch_host: bad argument");
   if (n > e->cfg.max_batch) return fail(DCU_ERR_INVALID, "dcu_infer_batch_host: n > max_batch");
