@@ -536,11 +536,14 @@ void tc_tile_arrangement(int nt, int hout, int wout, int* tr, int* tc) {
 int tc_supported_shape(int cin, int cout) {
   if (cin % 16 != 0 || cin > 256) return 0;
   if (cout == 64) return 64;
-  // 64 -> 128 layers (detector conv3a, RefineNet conv2a): K is only 4 chunks deep, so the un-overlapped epilogue of the single
-  // NT = 128 accumulator set costs more than reading the activations twice with double-buffered NT = 64 slices (DCU_NT64=0: off)
-  static const int nt64 = [] { const char* v = getenv("DCU_NT64"); return v ? atoi(v) : 1; }();
+  // Every layer runs in 64-channel slices (DCU_NT64: 0 = 128-channel slices wherever possible, 1 = only the 64 -> 128 layers in 64s,
+  // 2 = default).  A 128-channel slice owns all 512 TMEM columns (2 m-tiles x [main | correction] x 128), so its accumulators are
+  // single-buffered and the MMA warp waits for the epilogue's tcgen05.ld (64 B / cycle / SM: ~4 k cycles per tile, 14 - 17 % of the
+  // tile); 64-channel slices are double-buffered.  They read the activations once per slice, which the tile-major work order
+  // (conv_tc2.cu: slice_minor) turns into L2 hits.  A/B on one box, batch 256: + 1.1 % frames/s, + 1.5 % end to end.
+  static const int nt64 = [] { const char* v = getenv("DCU_NT64"); return v ? atoi(v) : 2; }();
   if (nt64 >= 1 && cin == 64 && cout == 128) return 64;
-  if ((nt64 >= 2 || tc2_segmented(cin)) && cout % 64 == 0 && cout <= 512) return 64;      // two-level accumulation keeps 64 running sums per epilogue thread
+  if ((nt64 >= 2 || tc2_segmented(cin)) && cout % 64 == 0 && cout <= 512) return 64;
   if (cout % 128 == 0 && cout <= 512) return 128;
   return 0;
 }

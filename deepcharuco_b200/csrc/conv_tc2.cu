@@ -53,7 +53,11 @@ namespace {
 constexpr int t2_threads(int cg) { return 128 + 256 * cg; }     // 4 control warps + 8 epilogue warps per channel group
 
 // WRES (weights resident): a 64 -> 64 layer's whole weight set (4 chunks x 3 kernel rows = 12 stages, 110.6 kB per rank) stays in
-// shared memory for the lifetime of the CTA instead of being re-fetched for every tile.  The kernel is bound by the shared-memory
+// shared memory for the lifetime of the CTA instead of being re-fetched for every tile.  UP + WRES (RefineNet convPa, the longest
+// kernel of the step): a work item is (tile, row phase) and needs the 8 stages of ITS row phase (4 chunks x 2 kernel rows x 4 blocks,
+// 98 kB per rank); every cluster keeps one row phase for its lifetime (even clusters phase 0, odd clusters phase 1), so those stay
+// resident too.  Without it the kernel asks L2 for 48 B / cycle / SM (83 kB of halo + 96 kB of weights per 3.7 k-cycle item) = 7.1 kB /
+// cycle chip-wide against a measured L2 limit of ~6.3 kB / cycle: tensor pipe 66 % active (profiles/r2_ncu_step_full.txt).  The kernel is bound by the shared-memory
 // data pipe (tensor-core operand fetches + fills, profiles/r1_ncu_conv_tc2.txt: 77 % + 23 %); the weight refills were 10 % of it.
 // MT_ = 1: one 128-pixel m-tile per CTA (16 x 8 pixels) instead of two -- launches with few work items (single frames) get twice
 // the items with half the MMA chain each; not for UP (its two m-tiles are the column phases) or FLAT.
@@ -63,7 +67,7 @@ struct Tc2Cfg {
   static constexpr int STAGE_BLOCKS = UP ? 4 : 3;                  // weight blocks per stage (one kernel row; UP: 2 taps x 2 column phases)
   static constexpr int NBUF = 512 / (MT * 2 * NT);
   static constexpr int A_STAGES = 4;
-  static constexpr int B_STAGES = WRES ? 12 : ((NT == 64) ? 6 : 4);
+  static constexpr int B_STAGES = WRES ? (UP ? 8 : 12) : ((NT == 64) ? 6 : 4);     // WRES: every stage of the layer (UP: of one row phase)
   static constexpr int MAX_HALO_PX = 34 * 10;
   static constexpr int A_STAGE_BYTES = 4 * MAX_HALO_PX * 16;
   static constexpr int B_MAIN_BYTES = 2 * NT * 16;                 // 2 k-groups x NT rows x 8 fp16 (this rank's half of [w_hi | w_lo])
@@ -345,6 +349,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int chunks = p.cin >> 4;
   const int halo_px = g.halo_w * g.halo_h;
+  // this cluster's work items: pt_begin, pt_begin + pt_step, ... < pt_end.  UP + WRES: the items of ONE row phase (slice-major numbering)
+  long long pt_begin = cluster_id, pt_end = g.total_pairs, pt_step = n_clusters;
+  if (UP && WRES) {
+    const long long ph = cluster_id & 1;
+    pt_begin = ph * g.pairs_per_slice + (cluster_id >> 1); pt_end = (ph + 1) * g.pairs_per_slice; pt_step = n_clusters >> 1;
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::A_STAGES; ++i) { mbar_init(&a_full[i], FIRST ? 12 : 1); mbar_init(&a_empty[i], 1); }
@@ -359,6 +369,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
   tc_fence_before();
   cluster_sync_all();                 // barriers of BOTH CTAs initialised before anyone signals across the pair
+  __syncthreads();                    // (implied by the cluster barrier; compute-sanitizer's racecheck only models the CTA barrier and
+                                      //  otherwise reports tcgen05.alloc's write of tmem_slot against the reads below)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -412,9 +424,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
       };
       asm volatile("griddepcontrol.wait;" ::: "memory");
-      prefetch(cluster_id);
+      prefetch(pt_begin);
       int st = 0; uint32_t ph = 0, wb = 0;
-      for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
+      for (long long pt = pt_begin; pt < pt_end; pt += pt_step) {
         const Tile2 c = decode_pair_tile(pt, rank, g);
         float* win = in_s + wb * Cfg::WIN_ELEMS;
         wb ^= 1u;
@@ -428,7 +440,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
         }
         asm volatile("bar.sync 1, 192;" ::: "memory");          // window (and, first time, the table) visible to the six producer warps
-        if (pt + n_clusters < g.total_pairs) prefetch(pt + n_clusters);
+        if (pt + pt_step < pt_end) prefetch(pt + pt_step);
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
           // this warp's 8 channels of the chunk: weights and BN constants into registers (FFMA operands), reused for all its pixels
@@ -492,7 +504,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");        // the activations are the previous kernel's output (weights are not: no wait there)
     int st = 0; uint32_t ph = 0;
-    for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
+    for (long long pt = pt_begin; pt < pt_end; pt += pt_step) {
       const Tile2 c = decode_pair_tile(pt, rank, g);
       for (int q = 0; q < chunks; ++q) {
         mbar_wait<200>(&a_empty[st], ph ^ 1u);
@@ -511,8 +523,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const CUtensorMap* wm = rank ? &tmap_w1 : &tmap_w0;
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(wm)) : "memory");
     int st = 0; uint32_t ph = 0;
-    for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
-      if (WRES && pt != cluster_id) break;              // resident weights (one slice): loaded with the first tile only
+    for (long long pt = pt_begin; pt < pt_end; pt += pt_step) {
+      if (WRES && pt != pt_begin) break;              // resident weights (one slice): loaded with the first tile only
       const int slice = pair_slice(pt, g);
       const int blk0 = slice * chunks * TAPS;
       for (int blk = 0; blk < chunks * TAPS; blk += SB) {
@@ -541,7 +553,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mt_off[mt] = g.flat ? (uint32_t)(mt * 128) : (uint32_t)(tri * 16 * g.halo_w + tci * 8);
     }
     int sa = 0, sb = 0, buf = 0; uint32_t pha = 0, phb = 0, phc = 0;
-    for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
+    for (long long pt = pt_begin; pt < pt_end; pt += pt_step) {
       const uint32_t ph_a = UP ? (uint32_t)(pair_slice(pt, g) & 1) : 0u;     // row phase of this work item
       for (int q = 0; q < chunks; ++q) {
         mbar_wait(&a_full[sa], pha);
@@ -556,7 +568,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
 #pragma unroll 1
         for (int ky = 0; ky < ROWS; ++ky) {
-          if (!WRES || pt == cluster_id) {
+          if (!WRES || pt == pt_begin) {
             mbar_wait(&b_full[sb], phb);
             tc_fence_after();
           }
@@ -604,7 +616,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t phc = 0;
     int buf = 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");        // (ordered anyway through the activation loads; keeps the stores formally after the wait)
-    for (long long pt = cluster_id; pt < g.total_pairs; pt += n_clusters) {
+    for (long long pt = pt_begin; pt < pt_end; pt += pt_step) {
       const Tile2 c = decode_pair_tile(pt, rank, g);
       if constexpr (SEG) {
         // drain every finished chunk of m-tile `grp` into registers (RN adds), releasing its accumulator set for the chunk after next
@@ -653,12 +665,31 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           inb = c.valid && (oy < p.hout) && (ox < p.wout);
         }
         float head_sum = 0.f;
-#pragma unroll (SEG ? NTG / CW : 1)
+        // EPI_PIPE (64-channel slices): the tcgen05.ld of column group cc + 1 is in flight while group cc goes through BN / ReLU / pool /
+        // split / stores.  tcgen05.ld moves 64 B / cycle / SM (~2 k cycles for the two m-tiles of a tile); load -> wait -> compute in
+        // series made the epilogue the pacing unit of the short work items (upsample-fused layers: 4 taps per chunk)
+        constexpr bool EPI_PIPE = !SEG && NT == 64;
+        float vb[EPI_PIPE ? 2 : 1][CW], sb[EPI_PIPE ? 2 : 1][CW];
+        if constexpr (EPI_PIPE) {
+          const uint32_t col0 = (uint32_t)((buf * MT + mt) * 2 * NT);
+          tmem_ld16_nowait(tmem_base + lane_addr + col0, vb[0]);
+          tmem_ld16_nowait(tmem_base + lane_addr + col0 + NT, sb[0]);
+        }
+#pragma unroll ((SEG || EPI_PIPE) ? NTG / CW : 1)
         for (int cc = 0; cc < NTG / CW; ++cc) {
           float v[CW];
           if constexpr (SEG) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) v[j] = racc[cc * CW + j] * p.wscale_inv;
+          } else if constexpr (EPI_PIPE) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (cc + 1 < NTG / CW) {
+              const uint32_t col = (uint32_t)((buf * MT + mt) * 2 * NT + (cc + 1) * CW);
+              tmem_ld16_nowait(tmem_base + lane_addr + col, vb[(cc + 1) & 1]);
+              tmem_ld16_nowait(tmem_base + lane_addr + col + NT, sb[(cc + 1) & 1]);
+            }
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] = (vb[cc & 1][j] + sb[cc & 1][j]) * p.wscale_inv;
           } else {
             float sm[CW];
             const uint32_t col = (uint32_t)((buf * MT + mt) * 2 * NT + cc * CW);
@@ -816,13 +847,18 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
   g.segc = std::max(1, std::min(p.cin <= 64 ? seg_c64 : seg_c128, p.cin / 16));
   g.seg0 = std::max(1, std::min(seg_first > 0 ? seg_first : g.segc, p.cin / 16));
   static const bool slice_minor = [] { const char* v = getenv("DCU_SLICE_MINOR"); return !v || atoi(v) != 0; }();
-  g.slice_minor = (slice_minor && n_slices > 1) ? 1 : 0;
+  g.slice_minor = (slice_minor && n_slices > 1 && !(UP && WRES)) ? 1 : 0;
   g.pairs_per_slice = (g.tiles_per_slice + 1) / 2;
   g.total_pairs = g.pairs_per_slice * g.slices;
   if (g.total_pairs <= 0) return cudaSuccess;
   // per pair work item and (16-channel chunk, tap, m-tile): one M=256 x N=2*NT x K=16 and one M=256 x N=NT x K=16 MMA
   if (issued_flops) *issued_flops = 2.0 * (double)g.total_pairs * (p.cin / 16) * (UP ? 4 : KS * KS) * Cfg::MT * 256.0 * 3.0 * NT * 16.0;
-  const long long clusters = g.total_pairs < sm_count / 2 ? g.total_pairs : sm_count / 2;
+  long long clusters = g.total_pairs < sm_count / 2 ? g.total_pairs : sm_count / 2;
+  if (UP && WRES) {       // one row phase per cluster: an even number of clusters, each phase with at least one item per cluster
+    if (g.slices != 2) return cudaErrorInvalidValue;
+    clusters = std::min<long long>(sm_count / 2, 2 * g.pairs_per_slice) & ~1LL;
+    if (clusters < 2) return cudaErrorInvalidValue;
+  }
   if (p.host_bn == nullptr) return cudaErrorInvalidValue;
   static const bool pdl = [] { const char* v = getenv("DCU_PDL"); return !v || atoi(v) != 0; }();
   cudaLaunchConfig_t cfg{};
@@ -889,6 +925,9 @@ cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const voi
     return launch_pair<64, 3, false, false, false, 2, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
   }
   if (up) {
+    static const bool wres_up = [] { const char* v = getenv("DCU_WRES_UP"); return !v || atoi(v) != 0; }();
+    if (nt == 64 && n_slices == 1 && p.cin == 64 && wres_up && !p.flat_in && sm_count >= 4)
+      return launch_pair<64, 3, true, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
     if (nt == 64) return launch_pair<64, 3, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
     if (nt == 128) return launch_pair<128, 3, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
     return cudaErrorInvalidValue;

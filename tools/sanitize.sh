@@ -10,6 +10,6 @@ TAG=${1:-rX}
 mkdir -p gpurun_out
 export DCU_GRAPH=0          # kernel-by-kernel launches (the sanitizer does not see inside graph replays as well)
 for tool in memcheck racecheck synccheck; do
-  (timeout 900 compute-sanitizer --tool $tool --error-exitcode 3 --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -25) > gpurun_out/${TAG}_sanitize_$tool.log 2>&1
+  (timeout 420 compute-sanitizer --tool $tool --error-exitcode 3 --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -25) > gpurun_out/${TAG}_sanitize_$tool.log 2>&1
   echo "== $tool: exit $? =="; tail -4 gpurun_out/${TAG}_sanitize_$tool.log
 done

@@ -117,7 +117,9 @@ for rep, name in (("conv_tc.ncu-rep", "ncu_conv_tc2.txt"), ("small.ncu-rep", "nc
 # ---- 3. copy the small text/JSON artefacts -------------------------------------------------------------------------------
 for src, dst in (("bench.json", "bench.json"), ("bench_reference.json", "bench_reference.json"), ("parity.json", "parity.json"),
                  ("bench_strict.json", "bench_strict_accumulation.json"), ("parity_strict.json", "parity_strict_accumulation.json"),
-                 ("parity_640.json", "parity_640x480.json"), ("mma_probe.json", "mma_probe.json"), ("mma_probe.log", "mma_probe.txt"),
+                 ("parity_640.json", "parity_640x480.json"), ("layer_table.json", "layer_table.json"),
+                 ("sanitize_memcheck.log", "sanitize_memcheck.txt"), ("sanitize_racecheck.log", "sanitize_racecheck.txt"),
+                 ("sanitize_synccheck.log", "sanitize_synccheck.txt"), ("mma_probe.json", "mma_probe.json"), ("mma_probe.log", "mma_probe.txt"),
                  ("tcstats.log", "tc_role_cycles.txt"), ("tc_vs_ffma.log", "tc_vs_ffma.txt"), ("pytest.log", "pytest_gpu.txt"),
                  ("smoke.log", "smoke.txt")):
     if os.path.isfile(G(src)):
