@@ -89,6 +89,7 @@ struct Tc2Geo {
   int flat, tile_px, lead;     // FLAT: pixels per CTA tile (256; UP: 128), pixels loaded ahead of the tile start (multiple of 16)
   int seg0, segc;              // SEG: 16-channel chunks in the FIRST segment of a tile and in every later segment (>= 1).  Each drain costs
                                // 128 TMEM columns x 128 lanes of tcgen05.ld per m-tile (64 B / cycle / SM): 4-chunk layers afford 2 segments
+  int epi_pipe;                // epilogue loads one column group ahead (launches with >= 4 work items per cluster)
   int slice_minor;             // work items ordered tile-major (item = pair * slices + slice): the slices of one pixel tile run at the same
                                // time on neighbouring clusters, so its halo is read from HBM once and from L2 by the other slices
   H2Layout out;                // output addressing
@@ -665,38 +666,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           inb = c.valid && (oy < p.hout) && (ox < p.wout);
         }
         float head_sum = 0.f;
-        // EPI_PIPE (64-channel slices): the tcgen05.ld of column group cc + 1 is in flight while group cc goes through BN / ReLU / pool /
-        // split / stores.  tcgen05.ld moves 64 B / cycle / SM (~2 k cycles for the two m-tiles of a tile); load -> wait -> compute in
-        // series made the epilogue the pacing unit of the short work items (upsample-fused layers: 4 taps per chunk)
-        constexpr bool EPI_PIPE = !SEG && NT == 64;
-        float vb[EPI_PIPE ? 2 : 1][CW], sb[EPI_PIPE ? 2 : 1][CW];
-        if constexpr (EPI_PIPE) {
-          const uint32_t col0 = (uint32_t)((buf * MT + mt) * 2 * NT);
-          tmem_ld16_nowait(tmem_base + lane_addr + col0, vb[0]);
-          tmem_ld16_nowait(tmem_base + lane_addr + col0 + NT, sb[0]);
-        }
-#pragma unroll ((SEG || EPI_PIPE) ? NTG / CW : 1)
-        for (int cc = 0; cc < NTG / CW; ++cc) {
-          float v[CW];
-          if constexpr (SEG) {
-#pragma unroll
-            for (int j = 0; j < CW; ++j) v[j] = racc[cc * CW + j] * p.wscale_inv;
-          } else if constexpr (EPI_PIPE) {
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (cc + 1 < NTG / CW) {
-              const uint32_t col = (uint32_t)((buf * MT + mt) * 2 * NT + (cc + 1) * CW);
-              tmem_ld16_nowait(tmem_base + lane_addr + col, vb[(cc + 1) & 1]);
-              tmem_ld16_nowait(tmem_base + lane_addr + col + NT, sb[(cc + 1) & 1]);
-            }
-#pragma unroll
-            for (int j = 0; j < CW; ++j) v[j] = (vb[cc & 1][j] + sb[cc & 1][j]) * p.wscale_inv;
-          } else {
-            float sm[CW];
-            const uint32_t col = (uint32_t)((buf * MT + mt) * 2 * NT + cc * CW);
-            tmem_ld16x2(tmem_base + lane_addr + col, v, tmem_base + lane_addr + col + NT, sm);
-#pragma unroll
-            for (int j = 0; j < CW; ++j) v[j] = (v[j] + sm[j]) * p.wscale_inv;
-          }
+        // one group of CW = 16 output channels of this thread's pixel: bias + BN + ReLU, then one of {fp32 logits, fused 1x1 head,
+        // 2x2 max-pool + store, 2x2 replicated store, plain store}
+        auto process = [&](const int cc, float (&v)[CW]) {
           const int ch0 = ch_base + cg * NTG + cc * CW;
           if (p.logits != nullptr) {
             if (inb) {
@@ -706,7 +678,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               for (int j = 0; j < CW; ++j)
                 if (ch0 + j < p.n_valid) o[(size_t)(ch0 + j) * plane_o] = v[j] + bn.v[0][ch0 + j];
             }
-            continue;
+            return;
           }
 #pragma unroll
           for (int j = 0; j < CW; j += 4) {
@@ -756,6 +728,52 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                          (size_t)oy * g.out.row + ox;
               store_h2_16(o, (size_t)g.out.lo, (size_t)g.out.plane, v);
             }
+          }
+        };
+        // EPI_PIPE (64-channel slices): the tcgen05.ld of column group cc + 1 is in flight while group cc goes through BN / ReLU / pool /
+        // split / stores.  tcgen05.ld moves 64 B / cycle / SM (~2 k cycles for the two m-tiles of a tile); load -> wait -> compute in
+        // series made the epilogue the pacing unit of the short work items (upsample-fused layers: 4 taps per chunk).  The pipelined
+        // loop is unrolled four times; launches with a handful of work items per cluster (single frames: 28 dependent kernels of
+        // ~10 us) take the compact loop instead -- the larger code cost them 10 % (instruction-cache misses of a cold kernel).
+#ifdef DCU_NO_EPI_PIPE
+        constexpr bool EPI_PIPE = false;
+#else
+        constexpr bool EPI_PIPE = !SEG && NT == 64;
+#endif
+        if constexpr (SEG) {
+#pragma unroll
+          for (int cc = 0; cc < NTG / CW; ++cc) {
+            float v[CW];
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] = racc[cc * CW + j] * p.wscale_inv;
+            process(cc, v);
+          }
+        } else if (EPI_PIPE && g.epi_pipe) {
+          float vb[2][CW], sb[2][CW];
+          const uint32_t col0 = tmem_base + lane_addr + (uint32_t)((buf * MT + mt) * 2 * NT);
+          tmem_ld16_nowait(col0, vb[0]);
+          tmem_ld16_nowait(col0 + NT, sb[0]);
+#pragma unroll
+          for (int cc = 0; cc < NTG / CW; ++cc) {
+            float v[CW];
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (cc + 1 < NTG / CW) {
+              tmem_ld16_nowait(col0 + (cc + 1) * CW, vb[(cc + 1) & 1]);
+              tmem_ld16_nowait(col0 + (cc + 1) * CW + NT, sb[(cc + 1) & 1]);
+            }
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] = (vb[cc & 1][j] + sb[cc & 1][j]) * p.wscale_inv;
+            process(cc, v);
+          }
+        } else {
+#pragma unroll 1
+          for (int cc = 0; cc < NTG / CW; ++cc) {
+            float v[CW], sm[CW];
+            const uint32_t col = (uint32_t)((buf * MT + mt) * 2 * NT + cc * CW);
+            tmem_ld16x2(tmem_base + lane_addr + col, v, tmem_base + lane_addr + col + NT, sm);
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] = (v[j] + sm[j]) * p.wscale_inv;
+            process(cc, v);
           }
         }
         if (p.head_w != nullptr) {
@@ -860,6 +878,7 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
     if (clusters < 2) return cudaErrorInvalidValue;
   }
   if (p.host_bn == nullptr) return cudaErrorInvalidValue;
+  g.epi_pipe = (g.total_pairs >= 4 * clusters) ? 1 : 0;
   static const bool pdl = [] { const char* v = getenv("DCU_PDL"); return !v || atoi(v) != 0; }();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)clusters * 2, 1, 1); cfg.blockDim = dim3(t2_threads(CG), 1, 1);
