@@ -1,24 +1,16 @@
-# scratch command file for `gpurun -- 'bash tools/_run.sh'`
-TAG=r2m
+# scratch command file for `gpurun --gpus 8 -- 'bash tools/_run.sh'`
+TAG=r2n
 mkdir -p gpurun_out
-(timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -6) > gpurun_out/${TAG}_pytest.log 2>&1
-tail -3 gpurun_out/${TAG}_pytest.log
-for i in 1 2; do (timeout 200 python tools/bench_single_frame.py 2>&1 | tail -1 | cut -c90-220); done
-(timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_launches.csv python tools/profile_step.py --batch 256 2>&1 | tail -1) > gpurun_out/${TAG}_ncu_list.log 2>&1
-python - <<PY
-import csv
-rows=[l for l in open("gpurun_out/${TAG}_launches.csv") if not l.startswith("==")]
-tot=0
-for r in csv.DictReader(rows):
-    v=float(r["Metric Value"].replace(",","")); u=r["Metric Unit"]; tot += v/1e3 if u=="ns" else (v*1e3 if u=="ms" else v)
-print("step kernel us (ncu):", round(tot,1))
-PY
-for i in a b; do
-(timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-configs 2>&1 | tail -1) > gpurun_out/${TAG}_bench_$i.json 2>gpurun_out/${TAG}_bench_$i.err
+nvidia-smi -L | wc -l
+(timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 tools/dist_check.py 2>&1 | grep -E "DIST_CHECK|Error|error" | head -5)
+(timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 8 --steps 20 --warmup 5 2>gpurun_out/${TAG}_bench8.err | tail -1) > gpurun_out/${TAG}_bench_8gpu.json
 python - <<PY
 import json
-try:
-    d=json.load(open("gpurun_out/${TAG}_bench_$i.json")); print("$i", round(d["value"]), "fps", round(d["ms_per_step"],3), "ms  e2e", round(d["e2e"]["value"]), "py", round(d["e2e_python"]["value"]), "frac", round(d["roofline"]["frac"],4))
-except Exception as e: print("$i", "ERR", e); print(open("gpurun_out/${TAG}_bench_$i.err").read()[-1500:])
+d=json.load(open("gpurun_out/${TAG}_bench_8gpu.json")); print("8gpu", round(d["value"]), "fps", round(d["ms_per_step"],3), "ms  e2e", round(d["e2e"]["value"]), "py", round(d["e2e_python"]["value"]), "one_batch", d.get("one_batch"), d["clocks"])
 PY
-done
+tail -3 gpurun_out/${TAG}_bench8.err
+(timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus 4 --steps 20 --warmup 5 2>/dev/null | tail -1) > gpurun_out/${TAG}_bench_4gpu.json
+python - <<PY
+import json
+d=json.load(open("gpurun_out/${TAG}_bench_4gpu.json")); print("4gpu", round(d["value"]), "fps", round(d["ms_per_step"],3), "ms  e2e", round(d["e2e"]["value"]), "py", round(d["e2e_python"]["value"]), "one_batch", d.get("one_batch"))
+PY
