@@ -20,7 +20,7 @@ CONV_DEFAULT = CONV_TCGEN05   # tcgen05 tensor-core path (fp16 hi/lo split); CON
 EXPORTS = [
     "dcu_create", "dcu_destroy", "dcu_detector_forward", "dcu_detector_forward_f32", "dcu_extract_patches",
     "dcu_decode_gather", "dcu_refine_forward", "dcu_infer_batch", "dcu_infer_batch_host", "dcu_infer_batch_host_bgr", "dcu_bgr_to_gray",
-    "dcu_debug_conv_layer", "dcu_debug_tc_stats", "dcu_set_conv_impl", "dcu_launch_count", "dcu_profile_enable", "dcu_profile_read", "dcu_profile_read_issued", "dcu_solve_pnp_batch", "dcu_solve_pnp_batch_host", "dcu_dc_metrics", "dcu_refinenet_metrics", "dcu_pixel_error", "dcu_synth_frames", "dcu_warp_perspective_u8", "dcu_profile_records", "dcu_detector_flops_per_frame",
+    "dcu_debug_conv_layer", "dcu_debug_tc_stats", "dcu_set_conv_impl", "dcu_launch_count", "dcu_profile_enable", "dcu_profile_read", "dcu_profile_read_issued", "dcu_solve_pnp_batch", "dcu_solve_pnp_batch_host", "dcu_dc_metrics", "dcu_refinenet_metrics", "dcu_pixel_error", "dcu_synth_frames", "dcu_warp_perspective_u8", "dcu_resize_u8", "dcu_profile_records", "dcu_detector_flops_per_frame",
     "dcu_refine_flops_per_patch", "dcu_last_error", "dcu_version",
 ]
 
@@ -76,6 +76,7 @@ def lib():
     L.dcu_infer_batch_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.dcu_infer_batch_host_bgr.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.dcu_bgr_to_gray.argtypes = [vp, vp, i32, vp, vp]
+    L.dcu_resize_u8.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     L.dcu_debug_conv_layer.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]
     L.dcu_debug_tc_stats.argtypes = [vp, i32, vp]
     L.dcu_set_conv_impl.argtypes = [vp, i32]

@@ -131,6 +131,7 @@ void launch_decode_gather(const DecodeParams& p, cudaStream_t s);
 size_t decode_smem_bytes(int cells);
 
 void launch_bgr_to_gray(const uint8_t* bgr, uint8_t* gray, long long n_px, cudaStream_t s);   // n_px % 4 == 0
+void launch_resize_linear_u8(const uint8_t* src, uint8_t* dst, const int* tab_dev, int n, int hs, int ws, int h, int w, int ch, cudaStream_t s);
 void launch_extract_patches(const float* image, int H, int W, const int32_t* xy, int k, float* patches, cudaStream_t s);
 
 // RefineNet tail: packed arg-max key -> (col,row) and refined (x,y)   (refinenet.py:111-114)

@@ -218,6 +218,37 @@ __global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, uint8_t* __r
     reinterpret_cast<uint32_t*>(gray)[i] = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
   }
 }
+// cv2.resize(src, (W, H), interpolation=cv2.INTER_LINEAR) for uint8 images when shrinking (the reference's evaluation loop resizes the
+// camera frame to the network input, inference.py:131-132), bit-exact with OpenCV's fixed-point path: 11-bit coefficients from float32
+// fractions (tables built on the host exactly like cv::resize builds them), horizontal pass in int, vertical pass
+//   dst = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2.
+// One thread per destination pixel (all channels); tab = [sx | ax0 | ax1] (W entries each) then [sy | ay0 | ay1] (H entries each).
+__global__ void resize_linear_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const int* __restrict__ tab, int n, int hs, int ws,
+                                        int h, int w, int ch) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * h * w) return;
+  const int x = (int)(i % w), y = (int)((i / w) % h);
+  const long long f = i / ((long long)w * h);
+  const int* tx = tab; const int* ty = tab + 3 * w;
+  const int sx = tx[x], a0 = tx[w + x], a1 = tx[2 * w + x], sy = ty[y], b0 = ty[h + y], b1 = ty[2 * h + y];
+  const int sx1 = min(sx + 1, ws - 1), sy1 = min(sy + 1, hs - 1);
+  const uint8_t* r0 = src + ((size_t)f * hs + sy) * ws * ch;
+  const uint8_t* r1 = src + ((size_t)f * hs + sy1) * ws * ch;
+  uint8_t* o = dst + (size_t)i * ch;
+  for (int c = 0; c < ch; ++c) {
+    const int h0 = (int)r0[sx * ch + c] * a0 + (int)r0[sx1 * ch + c] * a1;
+    const int h1 = (int)r1[sx * ch + c] * a0 + (int)r1[sx1 * ch + c] * a1;
+    const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    o[c] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+void launch_resize_linear_u8(const uint8_t* src, uint8_t* dst, const int* tab_dev, int n, int hs, int ws, int h, int w, int ch, cudaStream_t s) {
+  const long long total = (long long)n * h * w;
+  if (total <= 0) return;
+  resize_linear_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, dst, tab_dev, n, hs, ws, h, w, ch);
+}
+
 void launch_bgr_to_gray(const uint8_t* bgr, uint8_t* gray, long long n_px, cudaStream_t s) {
   if (n_px <= 0) return;
   long long b = ((n_px >> 2) + 255) / 256;

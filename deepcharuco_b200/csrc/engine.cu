@@ -337,6 +337,7 @@ struct DcuEngine {
   bool arg_heads = true;        // DCU_ARG_HEADS=0: heads write fp32 logits and the decode re-reads all 82 planes
   bool arg_heads_now = false;   // set around the fused pipeline's detector + decode
   DevBuf counts, offsets, total, kpts, patches, keys, refined, scan_state, frames;
+  DevBuf resize_tab; int resize_hs = 0, resize_ws = 0;      // coefficient tables of the last dcu_resize_u8 source size
   DevBuf synth_params, synth_lat, synth_m;   // dcu_synth_frames / dcu_warp_perspective_u8 scratch (grown on demand)
   DevBuf pnp_obj;               // [n_obj][2] board corner table of the last solve_pnp geometry
   int pnp_cols = 0, pnp_rows = 0; double pnp_sq = 0.0;
@@ -385,7 +386,7 @@ struct DcuEngine {
     if (gstream) cudaStreamDestroy(gstream);
     if (ev_start) cudaEventDestroy(ev_start);
     for (int i = 0; i < 2; ++i) { if (ev_done[i]) cudaEventDestroy(ev_done[i]); if (ev_free[i]) cudaEventDestroy(ev_free[i]); }
-    DevBuf* all[] = {&synth_params, &synth_lat, &synth_m, &loc_arg, &ids_arg, &pnp_obj, &flat8[0], &flat8[1], &flat8[2], &bgr, &c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
+    DevBuf* all[] = {&resize_tab, &synth_params, &synth_lat, &synth_m, &loc_arg, &ids_arg, &pnp_obj, &flat8[0], &flat8[1], &flat8[2], &bgr, &c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
                      &ids, &counts, &offsets, &total, &kpts, &patches, &keys, &refined, &scan_state, &frames};
     for (DevBuf* b : all) b->release();
     FirstLayer* fl[] = {&det_first, &ref_first};
@@ -1201,6 +1202,45 @@ int dcu_bgr_to_gray(DcuEngine* e, const uint8_t* bgr_dev, int n, uint8_t* gray_d
 static int infer_batch_host_impl(DcuEngine* e, const uint8_t* frames_host, int n, int channels, int dust_bin_ids, int use_refinenet,
                                  int32_t* counts_host, int32_t* offsets_host, int32_t* total_host, int32_t* kpts_host,
                                  float* refined_host, void* stream);
+
+// cv::resize's coefficient tables for INTER_LINEAR on 8-bit images (imgproc/resize.cpp): per destination index the source index and
+// the two 11-bit weights, from a float32 fraction of (d + 0.5) * scale - 0.5 clamped at the borders.
+static void resize_axis_table(int n_dst, int n_src, int* idx, int* a0, int* a1) {
+  const double scale = (double)n_src / n_dst;
+  for (int d = 0; d < n_dst; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int i = (int)std::floor(f);
+    f -= (float)i;
+    if (i < 0) { f = 0.f; i = 0; }
+    if (i >= n_src - 1) { f = 0.f; i = n_src - 1; }
+    auto sat = [](float v) { const long r = std::lrintf(v); return (int)std::max(-32768L, std::min(32767L, r)); };
+    idx[d] = i; a0[d] = sat((1.f - f) * 2048.f); a1[d] = sat(f * 2048.f);
+  }
+}
+
+int dcu_resize_u8(DcuEngine* e, const uint8_t* src_dev, int n, int src_h, int src_w, int channels, uint8_t* dst_dev, void* stream) {
+  if (!e || !src_dev || !dst_dev || n < 0 || (channels != 1 && channels != 3)) return fail(DCU_ERR_INVALID, "dcu_resize_u8: bad argument");
+  const int H = e->cfg.height, W = e->cfg.width;
+  if (src_h < H || src_w < W)
+    return fail(DCU_ERR_UNSUPPORTED, "dcu_resize_u8: only shrinking (source >= engine frame size) is bit-exact with cv2.resize; enlarge on the host");
+  if (n == 0) return DCU_OK;
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (e->resize_hs != src_h || e->resize_ws != src_w || !e->resize_tab.p) {
+    std::vector<int> tab(3 * (size_t)W + 3 * (size_t)H);
+    resize_axis_table(W, src_w, tab.data(), tab.data() + W, tab.data() + 2 * W);
+    resize_axis_table(H, src_h, tab.data() + 3 * W, tab.data() + 3 * W + H, tab.data() + 3 * W + 2 * H);
+    CK(cudaStreamSynchronize(s));                    // an earlier launch on this stream may still read the old table
+    e->resize_tab.release();
+    CK(e->resize_tab.alloc(tab.size() * 4));
+    CK(cudaMemcpy(e->resize_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    e->resize_hs = src_h; e->resize_ws = src_w;
+  }
+  launch_resize_linear_u8(src_dev, dst_dev, e->resize_tab.as<int>(), n, src_h, src_w, H, W, channels, s);
+  e->launches++;
+  CK(cudaGetLastError());
+  return DCU_OK;
+}
 
 int dcu_infer_batch_host(DcuEngine* e, const uint8_t* frames_host, int n, int dust_bin_ids, int use_refinenet,
                          int32_t* counts_host, int32_t* offsets_host, int32_t* total_host, int32_t* kpts_host,

@@ -20,7 +20,7 @@ from . import _native as N
 from . import weights_io
 
 __all__ = ["load_models", "infer_image", "infer_batch", "solve_pnp", "pred_to_keypoints", "extract_patches",
-           "pre_bgr_image", "draw_inner_corners"]
+           "pre_bgr_image", "draw_inner_corners", "resize_gpu"]
 
 
 def _default_conv_impl():
@@ -191,13 +191,53 @@ def _rows_to_frames(counts, offsets, kpts, refined):
     return out
 
 
-def infer_batch(frames, dust_bin_ids: int, deepc: DeepcHandle, refinenet: Optional[RefineHandle] = None):
+def _infer_batch_resized(frames, input_size, dust_bin_ids, deepc, refinenet):
+    """Camera frames larger than the network input: cv2.resize(frame, input_size, cv2.INTER_LINEAR) (inference.py:131-132) and
+    cv2.cvtColor(BGR2GRAY) (:40) both on the device (`dcu_resize_u8`, `dcu_bgr_to_gray`: bit-exact with cv2), then the pipeline."""
+    torch = _torch()
+    W, H = int(input_size[0]), int(input_size[1])
+    n, Hs, Ws = frames.shape[:3]
+    ch = 3 if frames.ndim == 4 else 1
+    ctx = deepc._ctx
+    eng = ctx.engine(H, W, max_batch=n)
+    dev = torch.device("cuda", ctx.device)
+    s = torch.cuda.current_stream(dev).cuda_stream
+    src = torch.from_numpy(np.ascontiguousarray(frames)).to(dev)
+    small = torch.empty((n, H, W, ch) if ch == 3 else (n, H, W), dtype=torch.uint8, device=dev)
+    N.check(N.lib().dcu_resize_u8(eng.handle, src.data_ptr(), n, Hs, Ws, ch, small.data_ptr(), s))
+    gray = small
+    if ch == 3:
+        gray = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
+        N.check(N.lib().dcu_bgr_to_gray(eng.handle, small.data_ptr(), n, gray.data_ptr(), s))
+    while True:
+        try:
+            o = eng.infer_batch_device(gray.data_ptr(), n, dust_bin_ids, refinenet is not None, s)
+        except N.CapacityError:
+            eng = ctx.engine(H, W, max_batch=n, max_patches=2 * eng.max_patches)
+            continue
+        total = int(o["total"].item())
+        if total <= eng.max_patches:
+            break
+        eng = ctx.engine(H, W, max_batch=n, max_patches=max(total, 2 * eng.max_patches))
+    counts, offsets = o["counts"][:n].cpu().numpy(), o["offsets"][:n].cpu().numpy()
+    kpts = o["kpts"][:total].cpu().numpy()
+    refined = o["refined"][:total].cpu().numpy() if refinenet is not None else None
+    return _rows_to_frames(counts, offsets, kpts, refined)
+
+
+def infer_batch(frames, dust_bin_ids: int, deepc: DeepcHandle, refinenet: Optional[RefineHandle] = None, input_size=None):
     """Batched form of infer_image: frames (N,H,W) uint8 grayscale or (N,H,W,3) BGR -> list of N keypoint arrays.
 
-    One H2D copy of the u8 frames, the fused GPU pipeline, one D2H copy of the packed result."""
+    One H2D copy of the u8 frames, the fused GPU pipeline, one D2H copy of the packed result.  input_size = (W, H): frames of
+    another (larger) size are first resized to the network input on the device like cv2.resize(frame, (W, H), cv2.INTER_LINEAR)
+    (the reference's evaluation loop, inference.py:131-132), bit-exact with cv2 when shrinking."""
     frames = np.asarray(frames)
     assert frames.dtype == np.uint8 and (frames.ndim == 3 or (frames.ndim == 4 and frames.shape[3] == 3)), \
         "frames must be (N,H,W) grayscale or (N,H,W,3) BGR uint8"
+    if input_size is not None and (frames.shape[2], frames.shape[1]) != (int(input_size[0]), int(input_size[1])):
+        if frames.shape[0] == 0:
+            return []
+        return _infer_batch_resized(frames, input_size, dust_bin_ids, deepc, refinenet)
     n, H, W = frames.shape[:3]          # BGR frames are converted on the device (OpenCV's fixed-point luma, bit-exact)
     if H % 8 or W % 8:
         raise ValueError(f"frame size {W}x{H} must be a multiple of 8 (three 2x2 pools, net.py:62,65,68)")
@@ -313,6 +353,24 @@ def extract_patches(img, keypoints, patch_size: int = 24):
     s = torch.cuda.current_stream(dev).cuda_stream
     N.check(N.lib().dcu_extract_patches(eng.handle, x.data_ptr(), xy.data_ptr(), k, out.data_ptr(), s))
     return out
+
+
+def resize_gpu(frames, input_size, device=0):
+    """cv2.resize(frame, (W, H), interpolation=cv2.INTER_LINEAR) for a batch of uint8 frames (N,Hs,Ws) or (N,Hs,Ws,3) on the B200;
+    bit-exact with cv2 when shrinking (the camera-to-network direction), DcuError (unsupported) when enlarging."""
+    torch = _torch()
+    frames = np.ascontiguousarray(frames, np.uint8)
+    W, H = int(input_size[0]), int(input_size[1])
+    n, Hs, Ws = frames.shape[:3]
+    ch = 3 if frames.ndim == 4 else 1
+    eng = _scratch_context(16, int(device)).engine(H, W)
+    dev = torch.device("cuda", int(device))
+    src = torch.from_numpy(frames).to(dev)
+    dst = torch.empty((n, H, W, ch) if ch == 3 else (n, H, W), dtype=torch.uint8, device=dev)
+    s = torch.cuda.current_stream(dev)
+    N.check(N.lib().dcu_resize_u8(eng.handle, src.data_ptr(), n, Hs, Ws, ch, dst.data_ptr(), s.cuda_stream))
+    s.synchronize()
+    return dst.cpu().numpy()
 
 
 def solve_pnp(keypoints, col_count, row_count, square_len, camera_matrix, dist_coeffs):

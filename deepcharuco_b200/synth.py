@@ -180,6 +180,13 @@ def make_frames_gpu(n, H=240, W=320, seed=0, n_boards=None, first_index=0, devic
     import torch
     from . import _native as N
     from .inference import _scratch_context
+    if H % 8 or W % 8 or H < 24 or W < 24:
+        raise ValueError(f"frame size {W}x{H} must be a multiple of 8 (>= 24), like the engine's")
+    if n_boards is None:
+        n_boards = 1 if (H <= 240 and W <= 320) else 4
+    if n <= 0:
+        empty = np.zeros((0, H, W), np.uint8)
+        return (torch.from_numpy(empty).to(torch.device("cuda", int(device))) if return_device else empty), np.zeros((0, n_boards, 16, 2))
     p = gpu_frame_params(n, H, W, seed, n_boards, first_index)
     dev = torch.device("cuda", int(device))
     key = (int(device),)

@@ -147,6 +147,13 @@ int dcu_infer_batch_host(DcuEngine* e, const uint8_t* frames_host, int n, int du
  * [N][H][W], OpenCV's 8-bit fixed-point luma, bit-exact.  (SURVEY.md 8f "next" row 1.) */
 int dcu_bgr_to_gray(DcuEngine* e, const uint8_t* bgr_dev, int n, uint8_t* gray_dev, void* stream);
 
+/* Replaces cv2.resize(img, (W, H), cv2.INTER_LINEAR) (the reference's evaluation loop resizes the camera frame to the network input,
+ * inference.py:131-132) on the device for uint8 images with 1 or 3 interleaved channels: src_dev [N][src_h][src_w][C] ->
+ * dst_dev [N][H][W][C] with H, W the engine's frame size.  Bit-exact with OpenCV's fixed-point path when SHRINKING (src >= dst in both
+ * dimensions, the camera-to-network direction); enlarging returns DCU_ERR_UNSUPPORTED (OpenCV's vector path rounds 0.1 % of the pixels
+ * differently there).  Together with dcu_bgr_to_gray this is the whole input stage of SURVEY.md 8f row 1. */
+int dcu_resize_u8(DcuEngine* e, const uint8_t* src_dev, int n, int src_h, int src_w, int channels, uint8_t* dst_dev, void* stream);
+
 /* dcu_infer_batch_host for BGR frames: frames_host uint8 [N][H][W][3]; the colour conversion runs on the device too. */
 int dcu_infer_batch_host_bgr(DcuEngine* e, const uint8_t* frames_host, int n, int dust_bin_ids, int use_refinenet,
                              int32_t* counts_host, int32_t* offsets_host, int32_t* total_host,

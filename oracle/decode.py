@@ -75,3 +75,38 @@ def marshal_keypoints(keypoints, ids_found):
     """inference.py:68-70 -- stable sort by id, rows [x, y, id]; float64 when refined, int64 when raw."""
     order = sorted(range(len(ids_found)), key=lambda i: ids_found[i])   # Python sorted is stable, as in the reference
     return np.array([[keypoints[i][0], keypoints[i][1], ids_found[i]] for i in order])
+
+
+def resize_linear_u8(src, dsize):
+    """cv2.resize(src, (W, H), interpolation=cv2.INTER_LINEAR) for uint8 (H,W) or (H,W,C) when shrinking -- the call of the reference's
+    evaluation loop (inference.py:131-132).  Third-party arithmetic (OpenCV imgproc/resize.cpp, 8-bit fixed-point path): per axis the
+    source index and two 11-bit weights from a float32 fraction of (d + 0.5) * scale - 0.5 (clamped at the borders), horizontal pass
+    in int, vertical pass (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2.  Pinned against cv2 in
+    tests/test_oracle_synth.py."""
+    Wd, Hd = dsize
+    s = src if src.ndim == 3 else src[..., None]
+    Hs, Ws, _ = s.shape
+
+    def coeffs(n_dst, n_src):
+        scale = np.float64(n_src) / n_dst
+        d = np.arange(n_dst)
+        f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+        i = np.floor(f).astype(np.int64)
+        f = (f - i.astype(np.float32)).astype(np.float32)
+        lo = i < 0
+        f = np.where(lo, np.float32(0), f); i = np.where(lo, 0, i)
+        hi = i >= n_src - 1
+        f = np.where(hi, np.float32(0), f); i = np.where(hi, n_src - 1, i)
+        a0 = np.clip(np.rint((np.float32(1.0) - f) * np.float32(2048)), -32768, 32767).astype(np.int64)
+        a1 = np.clip(np.rint(f * np.float32(2048)), -32768, 32767).astype(np.int64)
+        return i, a0, a1
+
+    sx, ax0, ax1 = coeffs(Wd, Ws)
+    sy, ay0, ay1 = coeffs(Hd, Hs)
+    sx1, sy1 = np.minimum(sx + 1, Ws - 1), np.minimum(sy + 1, Hs - 1)
+    S = s.astype(np.int64)
+    r0 = S[sy][:, sx] * ax0[None, :, None] + S[sy][:, sx1] * ax1[None, :, None]
+    r1 = S[sy1][:, sx] * ax0[None, :, None] + S[sy1][:, sx1] * ax1[None, :, None]
+    out = (((ay0[:, None, None] * (r0 >> 4)) >> 16) + ((ay1[:, None, None] * (r1 >> 4)) >> 16) + 2) >> 2
+    out = np.clip(out, 0, 255).astype(np.uint8)
+    return out if src.ndim == 3 else out[..., 0]

@@ -133,3 +133,25 @@ def test_empty_batch_and_bad_shapes(models):
     assert dc.infer_batch(np.zeros((0, 240, 320), np.uint8), 16, deepc, refinenet) == []
     with pytest.raises(Exception):
         dc.infer_batch(np.zeros((1, 100, 101), np.uint8), 16, deepc, refinenet)     # not a multiple of 8
+
+
+def test_device_resize_is_bit_exact_with_cv2_and_feeds_the_pipeline(models, golden_sample):
+    """SURVEY 8f row 1, the optional resize: cv2.resize(frame, (320, 240), INTER_LINEAR) (inference.py:131-132) on the device, bit-exact
+    with cv2 when shrinking; infer_batch(..., input_size) = resize + BGR->gray + pipeline equals the host-resized call."""
+    import cv2
+    from deepcharuco_b200.inference import resize_gpu
+    from deepcharuco_b200 import _native as N
+    deepc, refinenet = models
+    rng = np.random.default_rng(3)
+    for (Hs, Ws, ch) in ((1920, 2560, 3), (480, 640, 3), (720, 1280, 1), (300, 421, 3), (241, 323, 1), (240, 320, 3)):
+        src = rng.integers(0, 256, (2, Hs, Ws, ch) if ch == 3 else (2, Hs, Ws)).astype(np.uint8)
+        got = resize_gpu(src, (320, 240))
+        for i in range(2):
+            assert np.array_equal(got[i], cv2.resize(src[i], (320, 240), interpolation=cv2.INTER_LINEAR)), (Hs, Ws, ch)
+    with pytest.raises(N.DcuError):
+        resize_gpu(np.zeros((1, 120, 160), np.uint8), (320, 240))            # enlarging is not bit-exact with cv2: refused
+    big = cv2.resize(golden_sample["bgr"], (1280, 960), interpolation=cv2.INTER_CUBIC)      # a "camera frame" of the sample scene
+    small = cv2.resize(big, (320, 240), interpolation=cv2.INTER_LINEAR)
+    a = dc.infer_batch(big[None], 16, deepc, refinenet, input_size=(320, 240))[0]
+    b = dc.infer_batch(small[None], 16, deepc, refinenet)[0]
+    assert a.shape == b.shape and a.shape[0] >= 6 and np.array_equal(a, b)

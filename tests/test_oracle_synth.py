@@ -83,3 +83,14 @@ def test_oracle_frames_carry_detectable_boards(states):
             errs.append(np.linalg.norm(r[:, :2] - c[0][r[:, 2].astype(int)], axis=1).mean())
     assert np.mean(ks) > 10 and np.mean(errs) < 1.0
     assert np.float32(1.0 / 255.0).view(np.uint32) == 0x3B808081
+
+
+def test_resize_restatement_is_bit_exact_with_cv2_when_shrinking():
+    import cv2
+    from oracle.decode import resize_linear_u8
+    rng = np.random.default_rng(0)
+    for (Hs, Ws, C) in ((1920, 2560, 3), (480, 640, 3), (720, 1280, 1), (300, 421, 3), (241, 323, 1), (240, 320, 3)):
+        src = rng.integers(0, 256, (Hs, Ws, C)).astype(np.uint8)
+        if C == 1:
+            src = src[..., 0]
+        assert np.array_equal(resize_linear_u8(src, (320, 240)), cv2.resize(src, (320, 240), interpolation=cv2.INTER_LINEAR))
