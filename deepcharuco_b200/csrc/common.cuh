@@ -70,6 +70,9 @@ struct ConvParams {
   // are the data extents inside it); conv_tc2.cu FLAT mode.
   H2Layout out_layout;
   int flat_in, in_period, in_row;
+  // image count taken from DEVICE memory (sync-free detector -> RefineNet hand-off): when n_dev != nullptr the kernel processes
+  // clamp(*n_dev - n_off, 0, n) images; n stays the host-side upper bound that sizes tensor maps, layouts and the grid
+  const int* n_dev; int n_off;
   int mt1;                      // pair kernel: one m-tile (16 x 8 pixels) per CTA -- small launches; the caller's tensor map box is 10 x 18 pixels
   const struct TcBn* host_bn;   // host copy of bias / alpha / beta: the pair kernel takes them by value (constant bank)
   // FIRST mode of the pair kernel: `in` is unused; the 64 input channels are conv1a (+BN+ReLU) of the frames, computed in-kernel
@@ -99,6 +102,7 @@ struct FirstConvParams {
   const float* w;         // [9][64]
   const float* bias; const float* alpha; const float* beta;   // [64]
   int n, hin, win, hout, wout, pad;
+  const int* n_dev; int n_off;     // as ConvParams: process clamp(*n_dev - n_off, 0, n) images
 };
 void launch_conv_first(const FirstConvParams& p, cudaStream_t s);
 
@@ -136,7 +140,7 @@ void launch_extract_patches(const float* image, int H, int W, const int32_t* xy,
 
 // RefineNet tail: packed arg-max key -> (col,row) and refined (x,y)   (refinenet.py:111-114)
 void launch_refine_finalize(const unsigned long long* keys, const int32_t* xy, int xy_stride, int p,
-                            int32_t* corners, float* refined, cudaStream_t s);
+                            int32_t* corners, float* refined, cudaStream_t s, const int* n_dev = nullptr, int n_off = 0);
 
 // layout converters used by the debug/test entry point
 void launch_nchw_to_c4(const float* in, float* out, int n, int c, int h, int w, cudaStream_t s);

@@ -267,6 +267,7 @@ conv_first_kernel(FirstConvParams p, long long total_px) {
   if (p.in_u8 != nullptr)
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut_s[i] = p.lut[i];
   __syncthreads();
+  if (p.n_dev != nullptr) total_px = (long long)max(0, min(*p.n_dev - p.n_off, p.n)) * p.hout * p.wout;     // image count from the device
 
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_px;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -508,8 +509,9 @@ void launch_heads_1x1(const HeadParams& p, cudaStream_t s) {
 // RefineNet tail and layout converters
 // ---------------------------------------------------------------------------------------------------
 __global__ void refine_finalize_kernel(const unsigned long long* keys, const int32_t* xy, int xy_stride, int p,
-                                       int32_t* corners, float* refined) {
+                                       int32_t* corners, float* refined, const int* n_dev, int n_off) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev != nullptr) p = max(0, min(*n_dev - n_off, p));
   if (i >= p) return;
   const unsigned int idx = ~(unsigned int)(keys[i] & 0xffffffffull);
   const int col = (int)(idx & 63u), row = (int)(idx >> 6);          // speedy_bargmax2d: idx % 64, idx // 64
@@ -520,9 +522,9 @@ __global__ void refine_finalize_kernel(const unsigned long long* keys, const int
 }
 
 void launch_refine_finalize(const unsigned long long* keys, const int32_t* xy, int xy_stride, int p,
-                            int32_t* corners, float* refined, cudaStream_t s) {
+                            int32_t* corners, float* refined, cudaStream_t s, const int* n_dev, int n_off) {
   if (p <= 0) return;
-  refine_finalize_kernel<<<ceil_div(p, 128), 128, 0, s>>>(keys, xy, xy_stride, p, corners, refined);
+  refine_finalize_kernel<<<ceil_div(p, 128), 128, 0, s>>>(keys, xy, xy_stride, p, corners, refined, n_dev, n_off);
 }
 
 __global__ void nchw_to_c4_kernel(const float* in, float* out, int n, int c, int h, int w) {

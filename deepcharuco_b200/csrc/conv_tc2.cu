@@ -314,7 +314,7 @@ struct NoFirst {};
 template <int NT, int KS, bool UP, bool WRES, bool FIRST, int MT_ = 2, bool SEG = false, int CG = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(t2_threads(CG), 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w0,
-                const __grid_constant__ CUtensorMap tmap_w1, const ConvParams p, const Tc2Geo g, const __grid_constant__ TcBn bn,
+                const __grid_constant__ CUtensorMap tmap_w1, const ConvParams p, const Tc2Geo g_host, const __grid_constant__ TcBn bn,
                 const __grid_constant__ typename std::conditional<FIRST, FirstWeights, NoFirst>::type fw) {
   // bn: bias / BN scale / BN shift by value = constant bank.  The epilogue's channel index is warp-uniform, so these become
   // uniform constant loads instead of shared-memory reads (the shared-memory data pipe is what bounds this kernel).
@@ -344,6 +344,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   // (barrier init, TMEM allocation, tensor-map and weight prefetch) on SMs this grid leaves idle or has left; it blocks in its own
   // griddepcontrol.wait until this grid has completed and flushed.  Without the attribute both instructions are no-ops.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // Image count from device memory (ConvParams::n_dev; sync-free detector -> RefineNet hand-off): the geometry the host computed for
+  // the upper bound p.n shrinks to the images that exist.  No programmatic-dependency wait is needed before this read (it would
+  // cost the overlap of this kernel's prologue and weight prefetch with its predecessor's tail): the count is written by the decode
+  // kernel, and RefineNet's first kernel (conv_first_kernel) is an ordinary launch that starts only after the decode has completed;
+  // every kernel of this template comes later in the stream than that launch (engine.cu: refine_run).
+  Tc2Geo g = g_host;
+  int n_imgs = p.n;
+  if (p.n_dev != nullptr) {
+    n_imgs = max(0, min(*reinterpret_cast<const volatile int*>(p.n_dev) - p.n_off, p.n));
+    g.tiles_per_slice = g.flat ? ((long long)n_imgs * p.in_period + g.tile_px - 1) / g.tile_px : (long long)n_imgs * g.tiles_x * g.tiles_y;
+    g.pairs_per_slice = (g.tiles_per_slice + 1) / 2;
+    g.total_pairs = g.pairs_per_slice * g.slices;
+  }
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -654,7 +667,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           img = j / p.in_period;
           const int r = j - img * p.in_period;
           const int y = r / p.in_row, x = r - y * p.in_row;
-          inb = c.valid && img < p.n && y < (UP ? p.hin : p.hout) && x < (UP ? p.win : p.wout);
+          inb = c.valid && img < n_imgs && y < (UP ? p.hin : p.hout) && x < (UP ? p.win : p.wout);
           oy = UP ? 2 * y + (c.slice & 1) : y; ox = UP ? 2 * x + mt : x;
         } else {
           if (UP) {        // low-resolution pixel (y0 + prow, x0 + pcol), output phase (slice & 1, mt)

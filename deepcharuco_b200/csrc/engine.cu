@@ -353,6 +353,13 @@ struct DcuEngine {
   bool use_graphs = true;               // DCU_GRAPH=0: always launch kernel by kernel
   int graph_max_n = 8;
   int graph_hint = 0;                   // recent corner count per call, picks the graph's number of patch slots
+  // Sync-free detector -> RefineNet hand-off: RefineNet is enqueued right behind the decode for a number of
+  // 4096-patch chunks predicted from recent calls; its kernels take the true patch count from device memory, so a chunk does exactly
+  // the work that exists.  The host still learns the count (an event after the 4-byte copy, not a stream synchronisation: the GPU is
+  // already running RefineNet) and launches the rare chunk the prediction missed.  DCU_DEVICE_COUNT=0: read the count back first.
+  bool dev_count = true;
+  int patch_hint = 0;
+  cudaEvent_t ev_total = nullptr;
   // optional per-launch event timing (dcu_profile_*)
   struct ProfRec { cudaEvent_t a, b; double work; int cls; int shape[5]; double issued; };   // shape: cin, cout, hout, wout, n
   bool profiling = false;
@@ -385,6 +392,7 @@ struct DcuEngine {
     for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (gstream) cudaStreamDestroy(gstream);
     if (ev_start) cudaEventDestroy(ev_start);
+    if (ev_total) cudaEventDestroy(ev_total);
     for (int i = 0; i < 2; ++i) { if (ev_done[i]) cudaEventDestroy(ev_done[i]); if (ev_free[i]) cudaEventDestroy(ev_free[i]); }
     DevBuf* all[] = {&resize_tab, &synth_params, &synth_lat, &synth_m, &loc_arg, &ids_arg, &pnp_obj, &flat8[0], &flat8[1], &flat8[2], &bgr, &c1[0], &c1[1], &tc_loc.w, &tc_loc.bias, &tc_loc.ones, &tc_ids.w, &tc_ids.bias, &tc_ids.ones, &w_loc, &b_loc, &w_ids, &b_ids, &ref_head_w, &lut, &act[0], &act[1], &stage2_in, &heads, &loc,
                      &ids, &counts, &offsets, &total, &kpts, &patches, &keys, &refined, &scan_state, &frames};
@@ -562,6 +570,7 @@ struct FlatIn { int period, row; long long plane_px; };    // the layer's input 
 static long long flat_plane_px(int n, int period) { return (((long long)n * period + 15) / 16) * 16; }
 
 struct HeadFuse { const float* w = nullptr; float b = 0.f; unsigned long long* keys = nullptr; float* heat = nullptr; };
+struct DevCount { const int* p; int off; };      // image count in device memory: the launch processes clamp(*p - off, 0, n) images
 static unsigned long long* g_tc_stats = nullptr;   // device [8]; set by dcu_debug_tc_stats (profiling only)
 
 // hin x win: the layer's input size as the reference sees it.  fuse_up (tcgen05 pair kernel only): the upsampling between a
@@ -569,9 +578,9 @@ static unsigned long long* g_tc_stats = nullptr;   // device [8]; set by dcu_deb
 // consumer runs the phase-collapsed 2x2 kernels on it (`in` is then the hin/2 x win/2 tensor).
 static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, float* out, int n, int hin, int win,
                    const HeadFuse* hf, cudaStream_t s, bool fuse_up = false, const FlatIn* fin = nullptr,
-                   const H2Layout* lout = nullptr, const FirstIn* first = nullptr) {
+                   const H2Layout* lout = nullptr, const FirstIn* first = nullptr, const DevCount* dcnt = nullptr) {
   const bool up_in = fuse_up && l.ups_in;
-  if ((fin || lout || first) && !(impl == DCU_CONV_TCGEN05 && e->tc_pair)) return fail(DCU_ERR_INVALID, "flat layouts / conv1a fusion need the CTA-pair kernel");
+  if ((fin || lout || first || dcnt) && !(impl == DCU_CONV_TCGEN05 && e->tc_pair)) return fail(DCU_ERR_INVALID, "flat layouts / conv1a fusion / device-side counts need the CTA-pair kernel");
   ConvParams p{};
   p.in = in; p.out = out; p.bias = l.bias.as<float>(); p.alpha = l.alpha.as<float>(); p.beta = l.beta.as<float>();
   p.n = n; p.cin = l.cin; p.cout_total = l.cout; p.hin = up_in ? hin / 2 : hin; p.win = up_in ? win / 2 : win;
@@ -583,6 +592,7 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
   p.host_bn = &l.host_bn;
   if (fin) { p.flat_in = 1; p.in_period = fin->period; p.in_row = fin->row; }
   if (lout) p.out_layout = *lout;
+  if (dcnt) { p.n_dev = dcnt->p; p.n_off = dcnt->off; }
   if (first) { p.first_u8 = first->u8; p.first_f32 = first->f32; p.first_w = first->w; p.in = e->act[0].as<float>(); in = p.in; }
   if (n <= 0) return DCU_OK;
   e->prof_begin(0, 2.0 * 9.0 * (l.cin + (first ? 1 : 0)) * l.cout * (double)p.hout * p.wout * n, s, l.cin, l.cout, p.hout, p.wout, n);
@@ -624,10 +634,11 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
 }
 
 static int run_first(DcuEngine* e, const FirstLayer& f, const uint8_t* in_u8, const float* in_f32, float* out, int n,
-                     int hin, int win, int out_h2, cudaStream_t s, const H2Layout* lout = nullptr) {
+                     int hin, int win, int out_h2, cudaStream_t s, const H2Layout* lout = nullptr, const DevCount* dcnt = nullptr) {
   FirstConvParams p{};
   p.out_h2 = out_h2;
   if (lout) p.out_layout = *lout;
+  if (dcnt) { p.n_dev = dcnt->p; p.n_off = dcnt->off; }
   p.in_u8 = in_u8; p.in_f32 = in_f32; p.lut = e->lut.as<float>(); p.out = out; p.w = f.w.as<float>();
   p.bias = f.bias.as<float>(); p.alpha = f.alpha.as<float>(); p.beta = f.beta.as<float>();
   p.n = n; p.hin = hin; p.win = win; p.pad = f.pad; p.hout = hin + 2 * f.pad - 2; p.wout = win + 2 * f.pad - 2;
@@ -760,8 +771,10 @@ static int decode_group(DcuEngine* e, const float* loc, const float* ids, const 
 }
 
 // RefineNet on p patches (any p; processed in chunks of rp)
+// total_dev != nullptr (tcgen05 pair kernel with the flat / upsample-fused layouts only): p is an upper bound chosen by the host and every
+// kernel takes the true patch count from device memory -- no host round trip between the decode and RefineNet
 static int refine_run(DcuEngine* e, const float* patches, const int32_t* xy, int xy_stride, int p, int32_t* corners,
-                      float* refined, float* heat, cudaStream_t s) {
+                      float* refined, float* heat, cudaStream_t s, const int32_t* total_dev = nullptr, int p_begin = 0) {
   NvtxRange nvtx_range("dcu:refinenet");
   float* a0 = e->act[0].as<float>();
   float* a1 = e->act[1].as<float>();
@@ -770,8 +783,11 @@ static int refine_run(DcuEngine* e, const float* patches, const int32_t* xy, int
   const bool fu = e->fuse_up && e->tc_pair && e->conv_impl == DCU_CONV_TCGEN05 && e->ref[5].ups_in && e->ref[7].ups_in &&
                   e->ref[9].ups_in;
   const int chunk = fu ? e->rp : e->rp_plain;
-  for (int p0 = 0; p0 < p; p0 += chunk) {
+  if (total_dev && !(fu && e->flat && e->flat8[0].p)) return fail(DCU_ERR_INVALID, "device-side patch count needs the flat / upsample-fused RefineNet path");
+  for (int p0 = p_begin; p0 < p; p0 += chunk) {
     const int m = std::min(chunk, p - p0);
+    const DevCount dcv{total_dev, p0};
+    const DevCount* dc = total_dev ? &dcv : nullptr;
     unsigned long long* keys = e->keys.as<unsigned long long>() + p0;
     CK(cudaMemsetAsync(keys, 0, (size_t)m * sizeof(unsigned long long), s));
     if (fu && e->flat && e->flat8[0].p) {
@@ -781,13 +797,13 @@ static int refine_run(DcuEngine* e, const float* patches, const int32_t* xy, int
       const H2Layout l22 = h2_flat(64, 484, 22, pl22), l20 = h2_flat(64, 400, 20, pl20), l9 = h2_flat(128, 81, 9, pl9);
       const FlatIn f22{484, 22, pl22}, f20{400, 20, pl20}, f9{81, 9, pl9};
       float* g0 = e->flat8[0].as<float>(); float* g1 = e->flat8[1].as<float>(); float* g2 = e->flat8[2].as<float>();
-      if ((rc = run_first(e, e->ref_first, nullptr, patches + (size_t)p0 * 576, a0, m, 24, 24, 1, s, &l22))) return rc;  // conv1a -> 22
-      if ((rc = run_3x3(e, e->ref[0], e->conv_impl, a0, a1, m, 22, 22, nullptr, s, false, &f22, &l20))) return rc;     // conv1b -> 20
-      if ((rc = run_3x3(e, e->ref[1], e->conv_impl, a1, a0, m, 20, 20, nullptr, s, false, &f20, nullptr))) return rc;  // conv2a -> 18
-      if ((rc = run_3x3(e, e->ref[2], e->conv_impl, a0, g0, m, 18, 18, nullptr, s, false, nullptr, &l9))) return rc;   // conv2b -> 16 -> pool 8
-      if ((rc = run_3x3(e, e->ref[3], e->conv_impl, g0, g1, m, 8, 8, nullptr, s, false, &f9, &l9))) return rc;         // conv3a
-      if ((rc = run_3x3(e, e->ref[4], e->conv_impl, g1, g2, m, 8, 8, nullptr, s, true, &f9, &l9))) return rc;          // conv3b (-> up 16)
-      if ((rc = run_3x3(e, e->ref[5], e->conv_impl, g2, a0, m, 16, 16, nullptr, s, true, &f9, nullptr))) return rc;    // conv4a
+      if ((rc = run_first(e, e->ref_first, nullptr, patches + (size_t)p0 * 576, a0, m, 24, 24, 1, s, &l22, dc))) return rc;  // conv1a -> 22
+      if ((rc = run_3x3(e, e->ref[0], e->conv_impl, a0, a1, m, 22, 22, nullptr, s, false, &f22, &l20, nullptr, dc))) return rc;     // conv1b -> 20
+      if ((rc = run_3x3(e, e->ref[1], e->conv_impl, a1, a0, m, 20, 20, nullptr, s, false, &f20, nullptr, nullptr, dc))) return rc;  // conv2a -> 18
+      if ((rc = run_3x3(e, e->ref[2], e->conv_impl, a0, g0, m, 18, 18, nullptr, s, false, nullptr, &l9, nullptr, dc))) return rc;   // conv2b -> 16 -> pool 8
+      if ((rc = run_3x3(e, e->ref[3], e->conv_impl, g0, g1, m, 8, 8, nullptr, s, false, &f9, &l9, nullptr, dc))) return rc;         // conv3a
+      if ((rc = run_3x3(e, e->ref[4], e->conv_impl, g1, g2, m, 8, 8, nullptr, s, true, &f9, &l9, nullptr, dc))) return rc;          // conv3b (-> up 16)
+      if ((rc = run_3x3(e, e->ref[5], e->conv_impl, g2, a0, m, 16, 16, nullptr, s, true, &f9, nullptr, nullptr, dc))) return rc;    // conv4a
     } else {
     if ((rc = run_first(e, e->ref_first, nullptr, patches + (size_t)p0 * 576, a0, m, 24, 24, e->conv_impl == DCU_CONV_TCGEN05, s)))
       return rc;                                                                                  // conv1a -> 22
@@ -798,16 +814,16 @@ static int refine_run(DcuEngine* e, const float* patches, const int32_t* xy, int
     if ((rc = run_3x3(e, e->ref[4], e->conv_impl, a0, a1, m, 8, 8, nullptr, s, fu))) return rc;     // conv3b -> up 16
     if ((rc = run_3x3(e, e->ref[5], e->conv_impl, a1, a0, m, 16, 16, nullptr, s, fu))) return rc;   // conv4a
     }
-    if ((rc = run_3x3(e, e->ref[6], e->conv_impl, a0, a1, m, 16, 16, nullptr, s, fu))) return rc;   // conv4b -> up 32
-    if ((rc = run_3x3(e, e->ref[7], e->conv_impl, a1, a0, m, 32, 32, nullptr, s, fu))) return rc;   // conv5a
-    if ((rc = run_3x3(e, e->ref[8], e->conv_impl, a0, a1, m, 32, 32, nullptr, s, fu))) return rc;   // conv5b -> up 64
+    if ((rc = run_3x3(e, e->ref[6], e->conv_impl, a0, a1, m, 16, 16, nullptr, s, fu, nullptr, nullptr, nullptr, dc))) return rc;   // conv4b -> up 32
+    if ((rc = run_3x3(e, e->ref[7], e->conv_impl, a1, a0, m, 32, 32, nullptr, s, fu, nullptr, nullptr, nullptr, dc))) return rc;   // conv5a
+    if ((rc = run_3x3(e, e->ref[8], e->conv_impl, a0, a1, m, 32, 32, nullptr, s, fu, nullptr, nullptr, nullptr, dc))) return rc;   // conv5b -> up 64
     HeadFuse hf;
     hf.w = e->ref_head_w.as<float>(); hf.b = e->ref_head_b; hf.keys = keys;
     hf.heat = heat ? heat + (size_t)p0 * 4096 : nullptr;
-    if ((rc = run_3x3(e, e->ref[9], e->conv_impl, a1, nullptr, m, 64, 64, &hf, s, fu))) return rc;  // convPa + convPb + arg-max
+    if ((rc = run_3x3(e, e->ref[9], e->conv_impl, a1, nullptr, m, 64, 64, &hf, s, fu, nullptr, nullptr, nullptr, dc))) return rc;  // convPa + convPb + arg-max
     e->prof_begin(4, 0.0, s);
     launch_refine_finalize(keys, xy + (size_t)p0 * xy_stride, xy_stride, m, corners ? corners + 2 * (size_t)p0 : nullptr,
-                           refined + 2 * (size_t)p0, s);
+                           refined + 2 * (size_t)p0, s, total_dev, p0);
     e->prof_end(s);
     e->launches++;
     CK(cudaGetLastError());
@@ -951,6 +967,8 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
   TRYC(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
   TRYC(cudaEventCreateWithFlags(&e->ev_copy_start, cudaEventDisableTiming));
   if (const char* v = getenv("DCU_FUSE_FIRST")) e->fuse_first = atoi(v) != 0;
+  if (const char* v = getenv("DCU_DEVICE_COUNT")) e->dev_count = atoi(v) != 0;
+  TRYC(cudaEventCreateWithFlags(&e->ev_total, cudaEventDisableTiming));
   if (const char* v = getenv("DCU_GRAPH")) e->use_graphs = atoi(v) != 0;
   if (const char* v = getenv("DCU_GRAPH_MAX_N")) e->graph_max_n = std::max(0, atoi(v));
   TRYC(cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking));
@@ -1180,10 +1198,26 @@ int dcu_infer_batch(DcuEngine* e, const uint8_t* frames_dev, int n, int dust_bin
   }
   if (!use_refinenet) return DCU_OK;
   CK(cudaMemcpyAsync(e->h_total, total_dev, 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));   // corner count, as the reference's nonzero() does (model_utils.py:114)
+  // predicted hand-off: RefineNet goes into the stream before the host knows the corner count (see DcuEngine::dev_count)
+  const bool can_dev_count = e->dev_count && e->patch_hint > 0 && !e->profiling && e->conv_impl == DCU_CONV_TCGEN05 && e->tc_pair &&
+                             e->fuse_up && e->flat && e->flat8[0].p && e->ref[5].ups_in && e->ref[7].ups_in && e->ref[9].ups_in;
+  int launched = 0;
+  if (can_dev_count) {
+    CK(cudaEventRecord(e->ev_total, s));
+    const long long chunks = ((long long)e->patch_hint + e->rp - 1) / e->rp;
+    launched = (int)std::min<long long>(e->cfg.max_patches, chunks * e->rp);
+    rc = refine_run(e, e->patches.as<float>(), kpts_dev, 4, launched, nullptr, refined_dev, nullptr, s, total_dev);
+    if (rc) return rc;
+    CK(cudaEventSynchronize(e->ev_total));      // the count is on the host as soon as the decode has run; RefineNet is already queued behind it
+  } else {
+    CK(cudaStreamSynchronize(s));               // corner count first, as the reference's nonzero() does (model_utils.py:114)
+  }
   const int total = std::min(e->h_total[0], e->cfg.max_patches);
-  rc = refine_run(e, e->patches.as<float>(), kpts_dev, 4, total, nullptr, refined_dev, nullptr, s);
-  if (rc) return rc;
+  e->patch_hint = std::max(e->h_total[0], e->patch_hint - std::max(1, e->patch_hint / 16));      // recent maximum, decaying slowly
+  if (total > launched) {                        // first call, or more corners than predicted: the remaining chunks with the known count
+    rc = refine_run(e, e->patches.as<float>(), kpts_dev, 4, total, nullptr, refined_dev, nullptr, s, nullptr, launched);
+    if (rc) return rc;
+  }
   if (e->h_total[0] > e->cfg.max_patches)       // rows up to capacity are valid and refined; counts / offsets describe the full set
     return fail(DCU_ERR_CAPACITY, "corner count " + std::to_string(e->h_total[0]) + " exceeds max_patches " +
                                       std::to_string(e->cfg.max_patches));

@@ -124,8 +124,9 @@ int dcu_refine_forward(DcuEngine* e, const float* patches_dev, const int32_t* xy
                        int32_t* corners_dev, float* refined_dev, float* heat_dev, void* stream);
 
 /* Replaces the body of inference.infer_image (inference.py:41-60) for a batch resident in HBM:
- * detector -> decode+gather -> RefineNet.  The call synchronises `stream` once internally (after the
- * decode) to learn the corner count -- the reference does the same at model_utils.py:114.
+ * detector -> decode+gather -> RefineNet.  RefineNet is enqueued right behind the decode for a chunk count predicted from
+ * recent calls and takes the true patch count from device memory; the call waits (on an event, after the decode) only to
+ * learn the count and to launch a chunk the prediction missed -- the reference synchronises at model_utils.py:114.
  * Outputs (device): counts_dev [N], offsets_dev [N], total_dev [1], kpts_dev [max_patches][4] int32
  * {x, y, id, cell} and refined_dev [max_patches][2] float, both indexed by offsets_dev[f] + j.
  * use_refinenet == 0 skips the RefineNet leg (refinenet=None, inference.py:54).

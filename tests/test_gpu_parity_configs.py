@@ -126,3 +126,27 @@ def test_parity_other_n_ids(states, rows, extra):
     assert tot["K"] > 100
     parity.assert_parity(tot)
     parity.assert_no_flips(tot)
+
+
+def test_predicted_handoff_is_exact(states, golden_edge, monkeypatch):
+    """Sync-free detector -> RefineNet hand-off: RefineNet is enqueued for a number of 4096-patch chunks predicted from recent calls and its
+    kernels take the true patch count from device memory.  Sequence sparse -> crowded (prediction far too low: the missing chunks
+    are launched once the count is known) -> sparse (prediction far too high: whole chunks find no work) -> empty frames; every
+    result equals the one of an engine that reads the count back first (DCU_DEVICE_COUNT=0)."""
+    names = golden_edge["names"].tolist()
+    crowded = golden_edge["frames"][int(np.argmax(golden_edge["counts"]))]            # 12 boards: 192 corners
+    sparse = synth.make_frames(16, 240, 320, seed=31)
+    batches = [sparse, np.repeat(crowded[None], 64, axis=0), sparse, np.zeros((16, 240, 320), np.uint8), sparse[:5]]
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DCU_DEVICE_COUNT", mode)
+        e = N.Engine(states[0], states[1], 240, 320, 16, 0, max_batch=64, max_patches=16384)
+        try:
+            outs[mode] = [[a.copy() for a in e.infer_batch_host(b, 16, True)] for b in batches]
+        finally:
+            e.close()
+    assert int(outs["1"][1][0].sum()) == 64 * int(golden_edge["counts"].max()) > 3 * 4096 - 1
+    for got, want in zip(outs["1"], outs["0"]):
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+    assert names
