@@ -173,22 +173,19 @@ def pre_bgr_image(image):
 
 def _rows_to_frames(counts, offsets, kpts, refined):
     """Packed engine output -> per-frame arrays in the reference's format (inference.py:68-70):
-    float64 (K,3) [x, y, id] with RefineNet, int64 (K,3) without, np.array([]) when K == 0 (:51-52)."""
-    out = []
-    for c, o in zip(counts.tolist(), offsets.tolist()):
-        if c == 0:
-            out.append(np.array([]))
-            continue
-        rows = kpts[o:o + c]
-        if refined is not None:
-            r = np.empty((c, 3), np.float64)
-            r[:, :2] = refined[o:o + c]           # float32 -> float64, exact
-            r[:, 2] = rows[:, 2]
-        else:
-            r = np.empty((c, 3), np.int64)
-            r[:, 0], r[:, 1], r[:, 2] = rows[:, 0], rows[:, 1], rows[:, 2]
-        out.append(r)
-    return out
+    float64 (K,3) [x, y, id] with RefineNet, int64 (K,3) without, np.array([]) when K == 0 (:51-52).
+    One conversion for the whole batch; the per-frame arrays are slices of that fresh array (rows of a frame are contiguous)."""
+    counts = np.asarray(counts)
+    offsets = np.asarray(offsets)
+    total = int(counts.sum())
+    if refined is not None:
+        rows = np.empty((total, 3), np.float64)
+        rows[:, :2] = refined[:total]             # float32 -> float64, exact
+        rows[:, 2] = kpts[:total, 2]
+    else:
+        rows = kpts[:total, :3].astype(np.int64)
+    empty = np.array([])
+    return [rows[o:o + c] if c else empty.copy() for c, o in zip(counts.tolist(), offsets.tolist())]
 
 
 def _infer_batch_resized(frames, input_size, dust_bin_ids, deepc, refinenet):
