@@ -42,6 +42,11 @@ def _worker(rank, world, port, out_dir):
     for i, got in enumerate(full):
         want = _frame_result(loc[i % 3], ids[i % 3])
         assert got.shape == want.shape and np.array_equal(np.asarray(got, np.float64), np.asarray(want, np.float64))
+    # fewer frames than ranks (rank 1's shard is empty) and a frame without corners
+    one = sharding.infer_batch_distributed(frames[:1], 16, local_fn=lambda fr: [_frame_result(loc[i % 3], ids[i % 3]) for i in fr])
+    assert len(one) == 1 and np.array_equal(np.asarray(one[0], np.float64), np.asarray(_frame_result(loc[0], ids[0]), np.float64))
+    none = sharding.infer_batch_distributed(frames[:3], 16, local_fn=lambda fr: [np.array([]) for _ in fr])
+    assert len(none) == 3 and all(r.size == 0 for r in none)
     if rank == 0:
         merged = sharding.merge_shards([sharding.unpack_results(c, f, integer=True) for c, f in gathered])
         np.savez(os.path.join(out_dir, "merged.npz"), n=len(merged), tmax=t.numpy(),
