@@ -64,10 +64,10 @@ constexpr int t2_threads(int cg) { return 128 + 256 * cg; }     // 4 control war
 template <int NT, bool UP = false, bool WRES = false, int MT_ = 2>
 struct Tc2Cfg {
   static constexpr int MT = MT_;
-  static constexpr int STAGE_BLOCKS = UP ? 4 : 3;                  // weight blocks per stage (one kernel row; UP: 2 taps x 2 column phases)
+  static constexpr int STAGE_BLOCKS = UP ? 8 : 3;                  // weight blocks per stage (one kernel row; UP: the chunk's 2 x 2 taps x 2 column phases)
   static constexpr int NBUF = 512 / (MT * 2 * NT);
   static constexpr int A_STAGES = 4;
-  static constexpr int B_STAGES = WRES ? (UP ? 8 : 12) : ((NT == 64) ? 6 : 4);     // WRES: every stage of the layer (UP: of one row phase)
+  static constexpr int B_STAGES = WRES ? (UP ? 4 : 12) : (UP ? ((NT == 64) ? 3 : 2) : ((NT == 64) ? 6 : 4));     // WRES: every stage of the layer (UP: of one row phase)
   static constexpr int MAX_HALO_PX = 34 * 10;
   static constexpr int A_STAGE_BYTES = 4 * MAX_HALO_PX * 16;
   static constexpr int B_MAIN_BYTES = 2 * NT * 16;                 // 2 k-groups x NT rows x 8 fp16 (this rank's half of [w_hi | w_lo])
@@ -325,7 +325,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   constexpr int NTG = NT / CG;          // channels per epilogue thread
   // UP (input = 2x nearest upsampling of the tensor in HBM): per output phase (a, b) the 3x3 taps collapse to 2x2 taps on
   // the low-resolution tensor, so a weight stage is one of 2 kernel rows = 2 taps x 2 column phases (see header).
-  constexpr int ROWS = UP ? 2 : KS, TPR = UP ? 2 : KS, SB = Cfg::STAGE_BLOCKS, TAPS = ROWS * SB;
+  // weight stages per chunk (ROWS) and kernel rows inside one stage (KYS): 3 x 1 for a 3x3 kernel; UP: ONE stage with both rows of the
+  // collapsed 2x2 kernel -- 16 MMAs per elected issue region instead of 8 (every region costs the issuing warp ~100 cycles)
+  constexpr int ROWS = UP ? 1 : KS, KYS = UP ? 2 : 1, TPR = UP ? 2 : KS, SB = Cfg::STAGE_BLOCKS, TAPS = ROWS * SB;
   constexpr int ROWS_PER_BLOCK = Cfg::B_BLOCK_BYTES / 512;          // weight tensor map rows (512 B each) per block
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* a_smem = smem_raw;
@@ -586,22 +588,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             mbar_wait(&b_full[sb], phb);
             tc_fence_after();
           }
-          const uint32_t a_row = a_hi + (uint32_t)(g.a_org + (ky + (int)ph_a) * g.row_step);
           const uint32_t b_row = b_base0 + (uint32_t)sb * (Cfg::B_STAGE_BYTES >> 4);
           if (elect_one()) {
 #pragma unroll
-            for (int kx = 0; kx < TPR; ++kx) {
+            for (int kyy = 0; kyy < KYS; ++kyy) {
+              const int kyr = ky * KYS + kyy;                     // kernel row (UP: row of the collapsed 2x2 kernel)
+              const uint32_t a_row = a_hi + (uint32_t)(g.a_org + (kyr + (int)ph_a) * g.row_step);
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                // UP: m-tile mt is column phase b = mt of the same low-resolution tile: its own weight block, A window shifted by b
-                const uint32_t blk = UP ? (uint32_t)(kx * 2 + mt) : (uint32_t)kx;
-                const uint32_t b_main = bm_desc_lo0 + b_row + blk * (Cfg::B_BLOCK_BYTES >> 4);
-                const uint32_t b_x = bx_desc_lo0 + b_row + blk * (Cfg::B_BLOCK_BYTES >> 4) + (uint32_t)(Cfg::B_MAIN_BYTES >> 4);
-                const uint32_t d = tmem_u + (uint32_t)((buf * MT + mt) * 2 * NT);
-                const uint32_t da_hi = a_row + (uint32_t)kx + (UP ? (uint32_t)mt : mt_off[mt]);
-                const uint32_t da_lo = da_hi + 2u * (uint32_t)halo_px;
-                umma2_f16_w(d, da_hi, a_desc_hi, b_main, b_desc_hi, IDESC_2N, ((SEG ? (seg_open ? 0 : 1) : q) | ky | kx) ? 1u : 0u);   // [a_hi*w_hi | a_hi*w_lo]
-                umma2_f16_w(d + NT, da_lo, a_desc_hi, b_x, b_desc_hi, IDESC_1N, 1u);                        // + a_lo*w_hi
+              for (int kx = 0; kx < TPR; ++kx) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                  // UP: m-tile mt is column phase b = mt of the same low-resolution tile: its own weight block, A window shifted by b
+                  const uint32_t blk = UP ? (uint32_t)(kyy * 4 + kx * 2 + mt) : (uint32_t)kx;
+                  const uint32_t b_main = bm_desc_lo0 + b_row + blk * (Cfg::B_BLOCK_BYTES >> 4);
+                  const uint32_t b_x = bx_desc_lo0 + b_row + blk * (Cfg::B_BLOCK_BYTES >> 4) + (uint32_t)(Cfg::B_MAIN_BYTES >> 4);
+                  const uint32_t d = tmem_u + (uint32_t)((buf * MT + mt) * 2 * NT);
+                  const uint32_t da_hi = a_row + (uint32_t)kx + (UP ? (uint32_t)mt : mt_off[mt]);
+                  const uint32_t da_lo = da_hi + 2u * (uint32_t)halo_px;
+                  umma2_f16_w(d, da_hi, a_desc_hi, b_main, b_desc_hi, IDESC_2N, ((SEG ? (seg_open ? 0 : 1) : q) | kyr | kx) ? 1u : 0u);   // [a_hi*w_hi | a_hi*w_lo]
+                  umma2_f16_w(d + NT, da_lo, a_desc_hi, b_x, b_desc_hi, IDESC_1N, 1u);                        // + a_lo*w_hi
+                }
               }
             }
             if (!WRES) umma2_commit_mc(&b_empty[sb]);
@@ -931,7 +937,7 @@ int tc2_flat_rows(int in_row, int pad_or_up, int up) {
   const int back = pad_or_up ? in_row + 1 : 0, fwd = pad_or_up ? in_row + 1 : 2 * in_row + 2;
   return ceil_div(ceil_div(back, 16) * 16 + (up ? 128 : 256) + fwd, 16);
 }
-int tc2_stage_blocks(int up) { return up ? 4 : 3; }
+int tc2_stage_blocks(int up) { return up ? 8 : 3; }
 
 cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const void* tmap_a, const void* tmap_w0, const void* tmap_w1,
                             int sm_count, cudaStream_t s, double* issued_flops) {
