@@ -54,7 +54,7 @@ constexpr int t2_threads(int cg) { return 128 + 256 * cg; }     // 4 control war
 
 // WRES (weights resident): a 64 -> 64 layer's whole weight set (4 chunks x 3 kernel rows = 12 stages, 110.6 kB per rank) stays in
 // shared memory for the lifetime of the CTA instead of being re-fetched for every tile.  UP + WRES (RefineNet convPa, the longest
-// kernel of the step): a work item is (tile, row phase) and needs the 8 stages of ITS row phase (4 chunks x 2 kernel rows x 4 blocks,
+// kernel of the step): a work item is (tile, row phase) and needs the 4 stages of ITS row phase (4 chunks x [2 kernel rows x 4 blocks],
 // 98 kB per rank); every cluster keeps one row phase for its lifetime (even clusters phase 0, odd clusters phase 1), so those stay
 // resident too.  Without it the kernel asks L2 for 48 B / cycle / SM (83 kB of halo + 96 kB of weights per 3.7 k-cycle item) = 7.1 kB /
 // cycle chip-wide against a measured L2 limit of ~6.3 kB / cycle: tensor pipe 66 % active (profiles/r2_ncu_step_full.txt).  The kernel is bound by the shared-memory
@@ -324,7 +324,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   static_assert(CG == 1 || (SEG && CG == 2), "channel groups exist for the two-level accumulation only");
   constexpr int NTG = NT / CG;          // channels per epilogue thread
   // UP (input = 2x nearest upsampling of the tensor in HBM): per output phase (a, b) the 3x3 taps collapse to 2x2 taps on
-  // the low-resolution tensor, so a weight stage is one of 2 kernel rows = 2 taps x 2 column phases (see header).
+  // the low-resolution tensor (see header).
   // weight stages per chunk (ROWS) and kernel rows inside one stage (KYS): 3 x 1 for a 3x3 kernel; UP: ONE stage with both rows of the
   // collapsed 2x2 kernel -- 16 MMAs per elected issue region instead of 8 (every region costs the issuing warp ~100 cycles)
   constexpr int ROWS = UP ? 1 : KS, KYS = UP ? 2 : 1, TPR = UP ? 2 : KS, SB = Cfg::STAGE_BLOCKS, TAPS = ROWS * SB;
