@@ -43,6 +43,13 @@ def to_f32(x64, mode):
     return y
 
 
+LO8_SHIFT = None          # set to p: the a_lo x w_hi product runs on e4m3 operands (a_lo * 2^p, w_hi * 2^-p), --lo8 p
+
+
+def q8(x):
+    return x.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float()
+
+
 def conv_model(x, w, pad, mode, seg, taps_collapsed=None):
     """x (N,C,H,W) fp32, w (O,C,3,3) fp32 -> conv output (N,O,H',W') fp32 before bias, per the kernel's MMA order."""
     O, C = w.shape[0], w.shape[1]
@@ -52,6 +59,11 @@ def conv_model(x, w, pad, mode, seg, taps_collapsed=None):
     s = 2.0 ** np.floor(np.log2(32768.0 / mx))
     xh, xl = split_f16(x)
     wh, wl = split_f16(w * s)
+    wx = wh
+    if LO8_SHIFT is not None:
+        xl = q8(xl * 2.0 ** LO8_SHIFT) * 2.0 ** -LO8_SHIFT
+        wx = q8((w * s) * 2.0 ** -LO8_SHIFT) * 2.0 ** LO8_SHIFT
+    wx = wx.double()
     xh = F.pad(xh, (pad,) * 4).double()
     xl = F.pad(xl, (pad,) * 4).double()
     wh, wl = wh.double(), wl.double()
@@ -69,7 +81,7 @@ def conv_model(x, w, pad, mode, seg, taps_collapsed=None):
                 al = xl[:, cs, ky:ky + Ho, kx:kx + Wo]
                 pm = torch.einsum("nchw,oc->nohw", ah, wh[:, cs, ky, kx])
                 ps1 = torch.einsum("nchw,oc->nohw", ah, wl[:, cs, ky, kx])
-                ps2 = torch.einsum("nchw,oc->nohw", al, wh[:, cs, ky, kx])
+                ps2 = torch.einsum("nchw,oc->nohw", al, wx[:, cs, ky, kx])
                 main = to_f32(main.double() + pm, mode)
                 small = to_f32(small.double() + ps1, mode)
                 small = to_f32(small.double() + ps2, mode)
@@ -142,7 +154,9 @@ if __name__ == "__main__":
     ap.add_argument("--segs", default="0,9,3", help="MMAs per segment; 'a:b' = a for 64-channel inputs, b for 128-channel inputs")
     ap.add_argument("--patches", type=int, default=12)
     ap.add_argument("--skip-det", action="store_true")
+    ap.add_argument("--lo8", type=int, default=None, help="emulate an e4m3 a_lo x w_hi product with this power-of-two shift")
     a = ap.parse_args()
+    LO8_SHIFT = a.lo8
     frames = synth.make_frames(a.frames, seed=1)
     with torch.no_grad():
         x = torch.from_numpy(np.stack([oracle.pre_bgr_image(f) for f in frames]))
