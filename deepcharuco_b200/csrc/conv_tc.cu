@@ -536,14 +536,18 @@ void tc_tile_arrangement(int nt, int hout, int wout, int* tr, int* tc) {
 int tc_supported_shape(int cin, int cout) {
   if (cin % 16 != 0 || cin > 256) return 0;
   if (cout == 64) return 64;
-  // Every layer runs in 64-channel slices (DCU_NT64: 0 = 128-channel slices wherever possible, 1 = only the 64 -> 128 layers in 64s,
-  // 2 = default).  A 128-channel slice owns all 512 TMEM columns (2 m-tiles x [main | correction] x 128), so its accumulators are
-  // single-buffered and the MMA warp waits for the epilogue's tcgen05.ld (64 B / cycle / SM: ~4 k cycles per tile, 14 - 17 % of the
-  // tile); 64-channel slices are double-buffered.  They read the activations once per slice, which the tile-major work order
-  // (conv_tc2.cu: slice_minor) turns into L2 hits.  A/B on one box, batch 256: + 1.1 % frames/s, + 1.5 % end to end.
-  static const int nt64 = [] { const char* v = getenv("DCU_NT64"); return v ? atoi(v) : 2; }();
-  if (nt64 >= 1 && cin == 64 && cout == 128) return 64;
-  if ((nt64 >= 2 || tc2_segmented(cin)) && cout % 64 == 0 && cout <= 512) return 64;
+  // Slice width (DCU_NT64: 0 = 128-channel slices on two m-tiles per CTA wherever possible, 1 = as 0 but the 64 -> 128 layers in 64s,
+  // 2 = every layer in 64-channel slices, 3 = default: 128-channel slices on ONE m-tile per CTA for the plain 3x3 launches, 64-channel
+  // slices for the FLAT / upsample-fused / small ones -- the engine picks per launch, see run_3x3).  A 128-channel slice on two
+  // m-tiles owns all 512 TMEM columns (2 m-tiles x [main | correction] x 128): its accumulators are single-buffered and the MMA warp
+  // waits for the epilogue's tcgen05.ld (64 B / cycle / SM: ~4 k cycles per tile, 14 - 17 % of the tile).  64-channel slices are
+  // double-buffered (+ 1.1 % frames/s over mode 0), but their N = 64 correction MMA is operand-fetch bound (40 cycles of shared-memory
+  // reads for 32 of math).  One m-tile x 128 channels is double-buffered AND has no fetch-bound MMA: - 5 ... - 9 % on the detector's
+  // 128- and 512-channel layers, same box.
+  static const int nt64 = [] { const char* v = getenv("DCU_NT64"); return v ? atoi(v) : 3; }();
+  if (tc2_segmented(cin) && cout % 64 == 0 && cout <= 512) return 64;
+  if ((nt64 == 1 || nt64 == 2) && cin == 64 && cout == 128) return 64;
+  if (nt64 == 2 && cout % 64 == 0 && cout <= 512) return 64;
   if (cout % 128 == 0 && cout <= 512) return 128;
   return 0;
 }

@@ -323,6 +323,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   static_assert(!SEG || (NT == 64 && !FIRST && NBUF >= 2), "SEG: 64-channel slices, double-buffered accumulators, one m-tile per epilogue group");
   static_assert(CG == 1 || (SEG && CG == 2), "channel groups exist for the two-level accumulation only");
   constexpr int NTG = NT / CG;          // channels per epilogue thread
+  // one m-tile per CTA: the second group of four epilogue warps has no m-tile of its own and takes the upper half of the channels
+  constexpr bool HALF = MT == 1 && !SEG && !FIRST;
+  constexpr int NTE = HALF ? NT / 2 : NTG;
   // UP (input = 2x nearest upsampling of the tensor in HBM): per output phase (a, b) the 3x3 taps collapse to 2x2 taps on
   // the low-resolution tensor (see header).
   // weight stages per chunk (ROWS) and kernel rows inside one stage (KYS): 3 x 1 for a 3x3 kernel; UP: ONE stage with both rows of the
@@ -376,7 +379,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     for (int i = 0; i < Cfg::A_STAGES; ++i) { mbar_init(&a_full[i], FIRST ? 12 : 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < NBUF; ++i) mbar_init(&acc_full[i], 1);
-    for (int i = 0; i < NBUF * MT; ++i) mbar_init(&acc_empty[i], 256 * CG);      // epilogue threads of both CTAs (leader's copy is used)
+    for (int i = 0; i < NBUF * MT; ++i) mbar_init(&acc_empty[i], 256 * (HALF ? 2 : CG));      // epilogue threads of both CTAs (leader's copy is used)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -665,7 +668,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       const int ch_base = (UP ? (c.slice >> 1) : c.slice) * NT;
 #pragma unroll 1
-      for (int mt = grp; mt < MT; mt += (FIRST ? 1 : 2)) {
+      for (int mt = HALF ? 0 : grp; mt < MT; mt += ((FIRST || HALF) ? 1 : 2)) {
         int oy, ox, img = c.img;
         bool inb;
         if (g.flat) {    // pixel j of the run -> (image, y, x) by the input's period / row stride; wrap-around positions are dropped
@@ -688,7 +691,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // one group of CW = 16 output channels of this thread's pixel: bias + BN + ReLU, then one of {fp32 logits, fused 1x1 head,
         // 2x2 max-pool + store, 2x2 replicated store, plain store}
         auto process = [&](const int cc, float (&v)[CW]) {
-          const int ch0 = ch_base + cg * NTG + cc * CW;
+          const int ch0 = ch_base + cg * NTG + (HALF ? grp * NTE : 0) + cc * CW;
           if (p.logits != nullptr) {
             if (inb) {
               const size_t plane_o = (size_t)p.hout * p.wout;
@@ -757,7 +760,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #ifdef DCU_NO_EPI_PIPE
         constexpr bool EPI_PIPE = false;
 #else
-        constexpr bool EPI_PIPE = !SEG && NT == 64;
+        constexpr bool EPI_PIPE = !SEG && (NT == 64 || HALF);
 #endif
         if constexpr (SEG) {
 #pragma unroll
@@ -769,14 +772,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
         } else if (EPI_PIPE && g.epi_pipe) {
           float vb[2][CW], sb[2][CW];
-          const uint32_t col0 = tmem_base + lane_addr + (uint32_t)((buf * MT + mt) * 2 * NT);
+          const uint32_t col0 = tmem_base + lane_addr + (uint32_t)((buf * MT + mt) * 2 * NT + (HALF ? grp * NTE : 0));
           tmem_ld16_nowait(col0, vb[0]);
           tmem_ld16_nowait(col0 + NT, sb[0]);
 #pragma unroll
-          for (int cc = 0; cc < NTG / CW; ++cc) {
+          for (int cc = 0; cc < NTE / CW; ++cc) {
             float v[CW];
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (cc + 1 < NTG / CW) {
+            if (cc + 1 < NTE / CW) {
               tmem_ld16_nowait(col0 + (cc + 1) * CW, vb[(cc + 1) & 1]);
               tmem_ld16_nowait(col0 + (cc + 1) * CW + NT, sb[(cc + 1) & 1]);
             }
@@ -786,9 +789,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
         } else {
 #pragma unroll 1
-          for (int cc = 0; cc < NTG / CW; ++cc) {
+          for (int cc = 0; cc < NTE / CW; ++cc) {
             float v[CW], sm[CW];
-            const uint32_t col = (uint32_t)((buf * MT + mt) * 2 * NT + cc * CW);
+            const uint32_t col = (uint32_t)((buf * MT + mt) * 2 * NT + (HALF ? grp * NTE : 0) + cc * CW);
             tmem_ld16x2(tmem_base + lane_addr + col, v, tmem_base + lane_addr + col + NT, sm);
 #pragma unroll
             for (int j = 0; j < CW; ++j) v[j] = (v[j] + sm[j]) * p.wscale_inv;
@@ -842,7 +845,7 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
   }
   Tc2Geo g{};
   if (UP && (p.pad != 1 || p.pool || p.ups || p.hout != 2 * p.hin || p.wout != 2 * p.win)) return cudaErrorInvalidValue;
-  if (MT_ == 1 && (UP || p.flat_in)) return cudaErrorInvalidValue;
+  if (MT_ == 1 && (UP || p.flat_in || p.head_w != nullptr)) return cudaErrorInvalidValue;   // (fused head: all channels of a pixel in one thread)
   if (CG != 1 && p.head_w != nullptr) return cudaErrorInvalidValue;      // the fused 1x1 head sums over all channels of a pixel in one thread
   if (p.flat_in) {
     // the batch as one run of pixels; CTA tile = 256 consecutive pixels (UP: 128, the two m-tiles are the column phases)
@@ -977,7 +980,9 @@ cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const voi
                    : launch_pair<64, 3, false, false, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
   }
   if (p.mt1) {
-    if (nt != 64 || up) return cudaErrorInvalidValue;
+    if (up) return cudaErrorInvalidValue;
+    if (nt == 128) return launch_pair<128, 3, false, false, false, 1>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
+    if (nt != 64) return cudaErrorInvalidValue;
     return launch_pair<64, 3, false, false, false, 1>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
   }
   if (nt == 64 && n_slices == 1 && p.cin == 64 && wres_ok) return launch_pair<64, 3, false, true>(p, n_slices, ta, w0, w1, sm_count, s, issued_flops);
