@@ -66,9 +66,9 @@ struct Tc2Cfg {
   static constexpr int MT = MT_;
   static constexpr int STAGE_BLOCKS = UP ? 8 : 3;                  // weight blocks per stage (one kernel row; UP: the chunk's 2 x 2 taps x 2 column phases)
   static constexpr int NBUF = 512 / (MT * 2 * NT);
-  static constexpr int A_STAGES = 4;
+  static constexpr int A_STAGES = UP ? 6 : 4;                      // UP: 4 taps per chunk -> a chunk is consumed in ~900 cycles; six stages keep ~2.5 us of loads in flight
   static constexpr int B_STAGES = WRES ? (UP ? 4 : 12) : (UP ? ((NT == 64) ? 3 : 2) : ((NT == 64) ? 6 : 4));     // WRES: every stage of the layer (UP: of one row phase)
-  static constexpr int MAX_HALO_PX = 34 * 10;
+  static constexpr int MAX_HALO_PX = UP ? 240 : 34 * 10;           // UP: 10 x 18 low-resolution pixels (FLAT: up to 15 rows of 16)
   static constexpr int A_STAGE_BYTES = 4 * MAX_HALO_PX * 16;
   static constexpr int B_MAIN_BYTES = 2 * NT * 16;                 // 2 k-groups x NT rows x 8 fp16 (this rank's half of [w_hi | w_lo])
   static constexpr int B_X_BYTES = 2 * (NT / 2) * 16;              // 2 k-groups x NT/2 rows     (this rank's half of w_hi)
