@@ -167,7 +167,7 @@ int tc2_block_bytes(int nt);
 bool tc2_segmented(int cin);   // two-level accumulation for a layer with cin input channels (DCU_SEG policy) -> it runs in 64-channel slices
 int tc2_stage_blocks(int up);       // weight blocks per bulk-copy stage (tensor-map box)
 // up != 0: p.in is the LOW-resolution tensor (hin x win) whose 2x nearest upsampling is the layer's input; hout = 2*hin
-int tc2_flat_rows(int in_row, int pad_or_up, int up);   // FLAT mode: rows of 16 pixels per halo box (tensor-map box height)
+int tc2_flat_rows(int in_row, int pad_or_up, int tile128);   // FLAT mode: rows of 16 pixels per halo box (tensor-map box height); tile128: 128-pixel CTA tiles (UP / one m-tile)
 // issued_flops (optional): 2 x the MACs the tensor pipes execute for this launch (3 products, padded tiles included)
 cudaError_t launch_conv_tc2(const ConvParams& p, int n_slices, int up, const void* tmap_a, const void* tmap_w0, const void* tmap_w1,
                             int sm_count, cudaStream_t s, double* issued_flops = nullptr);

@@ -86,7 +86,7 @@ struct Tc2Geo {
   // A-operand addressing in 16-byte pixels: tap (ky, kx) of m-tile mt starts at a_org + ky*row_step + kx + mt_off;
   // sbo = distance between consecutive groups of 8 M rows.  Standard: row_step = sbo = halo_w, a_org = 0.
   int row_step, sbo, a_org;
-  int flat, tile_px, lead;     // FLAT: pixels per CTA tile (256; UP: 128), pixels loaded ahead of the tile start (multiple of 16)
+  int flat, tile_px, lead;     // FLAT: pixels per CTA tile (256; UP or one m-tile: 128), pixels loaded ahead of the tile start (multiple of 16)
   int seg0, segc;              // SEG: 16-channel chunks in the FIRST segment of a tile and in every later segment (>= 1).  Each drain costs
                                // 128 TMEM columns x 128 lanes of tcgen05.ld per m-tile (64 B / cycle / SM): 4-chunk layers afford 2 segments
   int epi_pipe;                // epilogue loads one column group ahead (launches with >= 4 work items per cluster)
@@ -845,18 +845,18 @@ cudaError_t launch_pair(const ConvParams& p, int n_slices, const CUtensorMap* ta
   }
   Tc2Geo g{};
   if (UP && (p.pad != 1 || p.pool || p.ups || p.hout != 2 * p.hin || p.wout != 2 * p.win)) return cudaErrorInvalidValue;
-  if (MT_ == 1 && (UP || p.flat_in || p.head_w != nullptr)) return cudaErrorInvalidValue;   // (fused head: all channels of a pixel in one thread)
+  if (MT_ == 1 && (UP || p.head_w != nullptr)) return cudaErrorInvalidValue;   // (fused head: all channels of a pixel in one thread)
   if (CG != 1 && p.head_w != nullptr) return cudaErrorInvalidValue;      // the fused 1x1 head sums over all channels of a pixel in one thread
   if (p.flat_in) {
     // the batch as one run of pixels; CTA tile = 256 consecutive pixels (UP: 128, the two m-tiles are the column phases)
     if (p.pool || p.ups || p.head_w || p.logits || p.in_period <= 0 || p.in_row <= 0) return cudaErrorInvalidValue;
     if ((long long)p.n * p.in_period + 1024 > 0x7fffffffLL) return cudaErrorInvalidValue;
     const int back = (UP || p.pad) ? p.in_row + 1 : 0;            // pixels a tap reaches behind its output position
-    g.flat = 1; g.tile_px = UP ? 128 : 256;
+    g.flat = 1; g.tile_px = (UP || MT_ == 1) ? 128 : 256;
     g.lead = ceil_div(back, 16) * 16;
     g.a_org = g.lead - back; g.row_step = p.in_row; g.sbo = 8;
     g.tr = 1; g.tc = 1;
-    g.halo_w = 16; g.halo_h = tc2_flat_rows(p.in_row, (UP || p.pad) ? 1 : 0, UP ? 1 : 0);
+    g.halo_w = 16; g.halo_h = tc2_flat_rows(p.in_row, (UP || p.pad) ? 1 : 0, (UP || MT_ == 1) ? 1 : 0);
     g.tiles_x = 1; g.tiles_y = 1;
     g.tiles_per_slice = ((long long)p.n * p.in_period + g.tile_px - 1) / g.tile_px;
     if (UP) n_slices *= 2;
@@ -936,9 +936,9 @@ bool tc2_segmented(int cin) {
   const int pol = tc2_seg_policy();
   return pol == 1 || (pol == 2 && cin >= 128);
 }
-int tc2_flat_rows(int in_row, int pad_or_up, int up) {
+int tc2_flat_rows(int in_row, int pad_or_up, int tile128) {
   const int back = pad_or_up ? in_row + 1 : 0, fwd = pad_or_up ? in_row + 1 : 2 * in_row + 2;
-  return ceil_div(ceil_div(back, 16) * 16 + (up ? 128 : 256) + fwd, 16);
+  return ceil_div(ceil_div(back, 16) * 16 + (tile128 ? 128 : 256) + fwd, 16);
 }
 int tc2_stage_blocks(int up) { return up ? 8 : 3; }
 

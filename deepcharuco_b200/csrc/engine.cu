@@ -613,12 +613,12 @@ static int run_3x3(DcuEngine* e, const Layer3x3& l, int impl, const float* in, f
     // fetch-bound MMA; conv_tc.cu tc_supported_shape) where the kernel has that form, in 64-channel slices otherwise
     static const bool nt128_mt1 = [] { const char* v = getenv("DCU_NT64"); return !v || atoi(v) == 3; }();
     if (nt128_mt1 && e->tc_pair && l.tc_nt == 128 && !use64) {
-      if (!up_in && !fin && !first) { p.mt1 = 1; g.tr = 1; g.tc = 1; }
+      if (!up_in && !first) { p.mt1 = 1; g.tr = 1; g.tc = 1; }
       else if (l.has_64) use64 = true;
     }
     CUtensorMap tm;
     int rc = fin ? make_tmap_flat(&tm, in, (long long)n * fin->period, l.cin, fin->plane_px,
-                                  tc2_flat_rows(fin->row, (up_in || l.pad) ? 1 : 0, up_in ? 1 : 0))
+                                  tc2_flat_rows(fin->row, (up_in || l.pad) ? 1 : 0, (up_in || p.mt1) ? 1 : 0))
              : up_in ? make_tmap(&tm, in, n, l.cin, p.hin, p.win, 10, 18)
                      : make_tmap(&tm, in, n, l.cin, hin, win, 8 * g.tc + 2, 16 * g.tr + 2);
     if (rc) return rc;
