@@ -80,7 +80,7 @@ struct ConvParams {
   const uint8_t* first_u8;              // [n][hin][win] u8 frames (normalised in-kernel), or
   const float* first_f32;               // [n][hin][win] already normalised images
 };
-struct TcBn { float v[3][512]; };   // [bias | alpha | beta][channel]
+struct TcBn { float v[3][512]; float head[64]; };   // [bias | alpha | beta][channel]; head: weights of a fused 1x1 head (64 -> 1), else unused
 struct FirstWeights { float w[9 * 64]; float bias[64], alpha[64], beta[64]; };   // conv1a: w[tap][channel], BN as y = fma(acc + bias, alpha, beta)
 
 // FFMA path: weights packed [cin/4][9 taps][4 cin][cout_total] with the cout axis permuted per 64-block

@@ -80,6 +80,14 @@ struct Tc2Cfg {
   static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + BAR_BYTES + WIN_BYTES + 1024;
 };
 
+// -DDCU_TC2_STATS: role-level cycle counters (MMA warp of every leader CTA, epilogue warp 4 of every leader CTA) for tools/tc_stats.py;
+// a profiling build only -- the shipped library compiles the counters out
+#ifdef DCU_TC2_STATS
+#define T2_STATS(...) __VA_ARGS__
+#else
+#define T2_STATS(...)
+#endif
+
 struct Tc2Geo {
   int tr, tc, halo_w, halo_h, tiles_x, tiles_y, slices;
   long long tiles_per_slice, pairs_per_slice, total_pairs;
@@ -572,23 +580,31 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mt_off[mt] = g.flat ? (uint32_t)(mt * 128) : (uint32_t)(tri * 16 * g.halo_w + tci * 8);
     }
     int sa = 0, sb = 0, buf = 0; uint32_t pha = 0, phb = 0, phc = 0;
+    T2_STATS(long long w_a = 0, w_b = 0, w_c = 0, t_w = 0; const long long t_start = clock64();)
     for (long long pt = pt_begin; pt < pt_end; pt += pt_step) {
       const uint32_t ph_a = UP ? (uint32_t)(pair_slice(pt, g) & 1) : 0u;     // row phase of this work item
       for (int q = 0; q < chunks; ++q) {
+        T2_STATS(t_w = clock64();)
         mbar_wait(&a_full[sa], pha);
+        T2_STATS(w_a += clock64() - t_w;)
         tc_fence_after();
         const uint32_t a_hi = a_desc_lo0 + a_base0 + (uint32_t)sa * (Cfg::A_STAGE_BYTES >> 4);
         const bool seg_open = !SEG || q == 0 || (q >= g.seg0 && (q - g.seg0) % g.segc == 0);
         const bool seg_close = !SEG || q == chunks - 1 || (q >= g.seg0 - 1 && (q - g.seg0 + 1) % g.segc == 0);
         if (SEG ? seg_open : q == 0) {          // SEG: a fresh accumulator set per segment
 #pragma unroll
+          T2_STATS(t_w = clock64();)
+#pragma unroll
           for (int mt = 0; mt < MT; ++mt) mbar_wait(&acc_empty[buf * MT + mt], phc ^ 1u);
+          T2_STATS(w_c += clock64() - t_w;)
           tc_fence_after();
         }
 #pragma unroll 1
         for (int ky = 0; ky < ROWS; ++ky) {
           if (!WRES || pt == pt_begin) {
+            T2_STATS(t_w = clock64();)
             mbar_wait(&b_full[sb], phb);
+            T2_STATS(w_b += clock64() - t_w;)
             tc_fence_after();
           }
           const uint32_t b_row = b_base0 + (uint32_t)sb * (Cfg::B_STAGE_BYTES >> 4);
@@ -625,11 +641,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       if (!SEG) { if (++buf == NBUF) { buf = 0; phc ^= 1u; } }
     }
+    T2_STATS(if (lane == 0 && p.stats) {
+      atomicAdd(p.stats + 0, (unsigned long long)(clock64() - t_start)); atomicAdd(p.stats + 1, (unsigned long long)w_a);
+      atomicAdd(p.stats + 2, (unsigned long long)w_b); atomicAdd(p.stats + 3, (unsigned long long)w_c); })
   } else if (warp >= 4 && (!FIRST || warp < 8) && (!SEG || (((warp - 4) >> 2) & 1) < MT)) {
     // ================= epilogue (both CTAs, each drains its own 128 TMEM lanes) =================
     constexpr int CW = 16;
     const int grp = (!FIRST && ((warp - 4) & 4)) ? 1 : 0;       // m-tile of this warp.  FIRST: warps 4-7 drain both m-tiles (warps 8-11 are the conv1a producers)
-    const int cg = (warp - 4) >> 3;                      // channel group: channels [cg * NTG, (cg + 1) * NTG) of the slice
+    const int cg = (CG == 1) ? 0 : (warp - 4) >> 3;      // channel group: channels [cg * NTG, (cg + 1) * NTG) of the slice
     float racc[SEG ? NTG : 1];                           // SEG: this thread's running sums (one pixel x NTG channels of m-tile `grp`)
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;
@@ -639,6 +658,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t phc = 0;
     int buf = 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");        // (ordered anyway through the activation loads; keeps the stores formally after the wait)
+    T2_STATS(long long w_e = 0, t_w = 0; const long long t_start = clock64();)
     for (long long pt = pt_begin; pt < pt_end; pt += pt_step) {
       const Tile2 c = decode_pair_tile(pt, rank, g);
       if constexpr (SEG) {
@@ -663,10 +683,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (++buf == NBUF) { buf = 0; phc ^= 1u; }
         }
       } else {
+        T2_STATS(t_w = clock64();)
         mbar_wait<200>(&acc_full[buf], phc);
+        T2_STATS(w_e += clock64() - t_w;)
         tc_fence_after();
       }
-      const int ch_base = (UP ? (c.slice >> 1) : c.slice) * NT;
+      // resident weights = ONE channel slice: every bias / BN / head constant of the unrolled epilogue below then has a compile-time
+      // offset in the constant bank and is an instruction operand.  Indexed constant loads (LDC) issue at ~1 per 8-15 cycles per SM:
+      // 104 of them per warp and tile made the epilogue the pacing unit of convPa + head (MMA warp 39 % in wait_epilogue).
+      const int ch_base = WRES ? 0 : (UP ? (c.slice >> 1) : c.slice) * NT;
 #pragma unroll 1
       for (int mt = HALF ? 0 : grp; mt < MT; mt += ((FIRST || HALF) ? 1 : 2)) {
         int oy, ox, img = c.img;
@@ -714,7 +739,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
           if (p.head_w != nullptr) {
 #pragma unroll
-            for (int j = 0; j < CW; ++j) head_sum = fmaf(v[j], __ldg(p.head_w + cc * CW + j), head_sum);
+            for (int j = 0; j < CW; ++j) head_sum = fmaf(v[j], bn.head[cc * CW + j], head_sum);
           } else if (p.pool) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
@@ -820,6 +845,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       if constexpr (!SEG) { if (++buf == NBUF) { buf = 0; phc ^= 1u; } }
     }
+    T2_STATS(if (rank == 0 && warp == 4 && lane == 0 && p.stats) {
+      atomicAdd(p.stats + 6, (unsigned long long)(clock64() - t_start)); atomicAdd(p.stats + 7, (unsigned long long)w_e); })
   }
 
   // ---- teardown: nobody may exit (or free TMEM) while the peer can still touch this CTA's barriers / tensor memory ----

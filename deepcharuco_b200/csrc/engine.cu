@@ -928,6 +928,7 @@ int dcu_create(const DcuConfig* cfg, const DcuConvLayer* D, int n_det, const Dcu
       return fail(DCU_ERR_INVALID, "dcu_create: RefineNet head shape");
     }
     TRYC(upload(e->ref_head_w, std::vector<float>(R[11].weight, R[11].weight + 64)));
+    std::memcpy(e->ref[9].host_bn.head, R[11].weight, 64 * sizeof(float));     // pair kernel: the fused head reads them from the constant bank
     e->ref_head_b = R[11].bias[0];
   }
   // (x - 128) / 255 in fp32 with a true division, as numpy does (model_utils.py:48-49)
