@@ -67,7 +67,10 @@ struct Tc2Cfg {
   static constexpr int STAGE_BLOCKS = UP ? 8 : 3;                  // weight blocks per stage (one kernel row; UP: the chunk's 2 x 2 taps x 2 column phases)
   static constexpr int NBUF = 512 / (MT * 2 * NT);
   static constexpr int A_STAGES = UP ? 6 : 4;                      // UP: 4 taps per chunk -> a chunk is consumed in ~900 cycles; six stages keep ~2.5 us of loads in flight
-  static constexpr int B_STAGES = WRES ? (UP ? 4 : 12) : (UP ? ((NT == 64) ? 3 : 2) : ((NT == 64) ? 6 : 4));     // WRES: every stage of the layer (UP: of one row phase)
+  // WRES: every stage of the layer (UP: of one row phase).  Streamed weights: as many stages as shared memory holds -- the MMA warp of
+  // the streamed launches spent 27-40 % of its time waiting for weight stages (tools/tc_stats.py), i.e. ~1.4 us of loads in flight
+  // did not cover the L2 latency under load
+  static constexpr int B_STAGES = WRES ? (UP ? 4 : 12) : (UP ? ((NT == 64) ? 5 : 2) : ((NT == 64) ? 6 : (MT_ == 1 ? 7 : 4)));
   static constexpr int MAX_HALO_PX = UP ? 240 : 34 * 10;           // UP: 10 x 18 low-resolution pixels (FLAT: up to 15 rows of 16)
   static constexpr int A_STAGE_BYTES = 4 * MAX_HALO_PX * 16;
   static constexpr int B_MAIN_BYTES = 2 * NT * 16;                 // 2 k-groups x NT rows x 8 fp16 (this rank's half of [w_hi | w_lo])
@@ -78,6 +81,7 @@ struct Tc2Cfg {
   static constexpr int WIN_ELEMS = 36 * 12;                        // FIRST: input window (halo + 2) of the largest tile arrangement
   static constexpr int WIN_BYTES = 2 * WIN_ELEMS * 4 + 768 * 4;    // two windows (double-buffered) + conv1a's weight / BN table, fp32
   static constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + BAR_BYTES + WIN_BYTES + 1024;
+  static_assert(SMEM_BYTES <= 232448, "227 kB of shared memory per CTA");
 };
 
 // -DDCU_TC2_STATS: role-level cycle counters (MMA warp of every leader CTA, epilogue warp 4 of every leader CTA) for tools/tc_stats.py;
