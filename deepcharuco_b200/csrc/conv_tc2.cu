@@ -59,8 +59,13 @@ constexpr int t2_threads(int cg) { return 128 + 256 * cg; }     // 4 control war
 // resident too.  Without it the kernel asks L2 for 48 B / cycle / SM (83 kB of halo + 96 kB of weights per 3.7 k-cycle item) = 7.1 kB /
 // cycle chip-wide against a measured L2 limit of ~6.3 kB / cycle: tensor pipe 66 % active (profiles/r2_ncu_step_full.txt).  The kernel is bound by the shared-memory
 // data pipe (tensor-core operand fetches + fills, profiles/r1_ncu_conv_tc2.txt: 77 % + 23 %); the weight refills were 10 % of it.
-// MT_ = 1: one 128-pixel m-tile per CTA (16 x 8 pixels) instead of two -- launches with few work items (single frames) get twice
-// the items with half the MMA chain each; not for UP (its two m-tiles are the column phases) or FLAT.
+// (The 66 % on convPa turned out to be its epilogue: indexed constant loads, see `ch_base` in the kernel.)
+// MT_ = 1: one 128-pixel m-tile per CTA (16 x 8 pixels, FLAT: a run of 128 pixels) instead of two; not for UP (its two m-tiles are the
+// column phases).  Two uses: (a) NT = 64, launches with few work items (single frames): twice the items with half the MMA chain each;
+// (b) NT = 128, the default for 128- / 512-channel layers: 256 TMEM columns per accumulator set, so the sets are double-buffered like
+// NT = 64's, and both MMAs of a tap are math-bound (N = 256 and 128; at NT = 64 the N = 64 correction MMA reads 5 kB of operands from
+// shared memory, 40 cycles, for 32 cycles of math).  The second group of epilogue warps, which has no m-tile, takes the upper half of
+// the channels (HALF in the kernel).
 template <int NT, bool UP = false, bool WRES = false, int MT_ = 2>
 struct Tc2Cfg {
   static constexpr int MT = MT_;
